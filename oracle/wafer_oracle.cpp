@@ -508,11 +508,15 @@ int wo_potential(const wo_grid* g, int kind, double sig, double* v) {
             return i == n - 1 ? extent : -extent + (double)i * step;  // numpy.linspace semantics
         };
         auto sech2 = [](double u) { const double s = 1. / std::cosh(u); return s * s; };
-        for (size_t i = 0; i < d.nx; ++i)
-            for (size_t j = 0; j < d.ny; ++j)
-                for (size_t k = 0; k < d.nz; ++k)
-                    v[d.p(i + d.e, j + d.e, k + d.e)] =
-                        coeff * sech2(axis(d.nx, i)) + coeff * sech2(axis(d.ny, j)) + coeff * sech2(axis(d.nz, k));
+        // per-axis terms coeff*sech^2 (each site's value is (tx + ty) + tz, the script's left-to-right sum)
+        std::vector<double> tx(d.nx), ty(d.ny), tz(d.nz);
+        for (size_t i = 0; i < d.nx; ++i) tx[i] = coeff * sech2(axis(d.nx, i));
+        for (size_t j = 0; j < d.ny; ++j) ty[j] = coeff * sech2(axis(d.ny, j));
+        for (size_t k = 0; k < d.nz; ++k) tz[k] = coeff * sech2(axis(d.nz, k));
+#pragma omp parallel for collapse(2) schedule(static)
+        for (long long i = 0; i < (long long)d.nx; ++i)
+            for (long long j = 0; j < (long long)d.ny; ++j)
+                for (size_t k = 0; k < d.nz; ++k) v[d.p(i + d.e, j + d.e, k + d.e)] = tx[i] + ty[j] + tz[k];
         return 0;
     }
     double probe;

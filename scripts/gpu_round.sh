@@ -1,0 +1,25 @@
+#!/bin/bash
+# One GPU-box session: parity tests, smoke, bench lines, ncu launch list + full capture of the sweep kernel.
+# Usage (under gpurun): bash scripts/gpu_round.sh <label> [stages...]   stages: test smoke bench benchab ncu
+set -u
+LABEL=${1:-run}; shift || true
+STAGES=${*:-"test smoke bench benchab ncu"}
+OUT=gpurun_out/$LABEL
+mkdir -p "$OUT"
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > "$OUT/gpu.csv" 2>&1
+for s in $STAGES; do
+  case $s in
+    test)   timeout 1500 python -m pytest tests -m gpu -x -q > "$OUT/pytest_gpu.log" 2>&1; echo "pytest rc=$?" | tee -a "$OUT/rc.log"; tail -5 "$OUT/pytest_gpu.log";;
+    smoke)  timeout 300 python __graft_entry__.py smoke > "$OUT/smoke.log" 2>&1; echo "smoke rc=$?" | tee -a "$OUT/rc.log"; tail -3 "$OUT/smoke.log";;
+    bench)  timeout 900 python bench.py --steps 3 --warmup 3 > "$OUT/bench.json" 2> "$OUT/bench.err"; echo "bench rc=$?" | tee -a "$OUT/rc.log"; cat "$OUT/bench.json"; tail -3 "$OUT/bench.err";;
+    benchab) timeout 600 python bench.py --steps 3 --warmup 3 --flags 1 --no-e2e --no-cpu > "$OUT/bench_ab.json" 2> "$OUT/bench_ab.err"; echo "benchab rc=$?" | tee -a "$OUT/rc.log"; cat "$OUT/bench_ab.json";;
+    ref)    timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > "$OUT/bench_ref.json" 2> "$OUT/bench_ref.err"; echo "ref rc=$?" | tee -a "$OUT/rc.log"; cat "$OUT/bench_ref.json";;
+    ncu)
+      timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/launches.csv" \
+        python bench.py --grid 512 --sweeps 20 --steps 2 --warmup 1 --no-e2e --no-cpu --no-512 > "$OUT/ncu_launch_bench.log" 2>&1
+      echo "ncu-launches rc=$?" | tee -a "$OUT/rc.log"
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:sweep -s 30 -c 2 -f -o "$OUT/sweep_full" \
+        python bench.py --grid 512 --sweeps 20 --steps 2 --warmup 1 --no-e2e --no-cpu --no-512 > "$OUT/ncu_full_bench.log" 2>&1
+      echo "ncu-full rc=$?" | tee -a "$OUT/rc.log";;
+  esac
+done

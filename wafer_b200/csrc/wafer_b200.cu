@@ -1,0 +1,805 @@
+// wafer_b200.cu — context, stream orchestration and the C ABI of include/wafer_b200.h.
+//
+// One wafer_ctx = one GPU = one x-slab of the lattice.  The reference functions each entry point replaces are
+// cited in the header; the driver loop `wafer_solve` restates src/grid.rs:50-246 on top of them.
+#include "../../include/wafer_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "generators.cuh"
+#include "kernels.cuh"
+#include "nccl_dyn.h"
+
+using namespace wafer;
+
+namespace {
+std::string g_create_error;
+
+// scalar slots in ctx->scal (device doubles)
+enum { SL_OBS = 0, SL_NORM = 4, SL_TMP = 5, SL_DOT = 8, SL_COUNT = 8 + 256 };
+}  // namespace
+
+struct wafer_ctx {
+    wafer_params p{};
+    Geom g{};
+    int dev = 0, sm_count = 0;
+    int rank = 0, world = 1;
+    bool onfly = true;
+    cudaStream_t s_main = nullptr, s_halo = nullptr;
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_main = nullptr, ev_halo = nullptr;
+    double* psi[2] = {nullptr, nullptr};
+    int cur = 0;
+    double *v = nullptr, *a = nullptr, *b = nullptr, *potsub_arr = nullptr;
+    int potsub_mode = 0;
+    double potsub_scalar = 0.0;
+    std::vector<double*> lowers;
+    double* partials = nullptr;
+    long long partials_cap = 0;
+    double* scal = nullptr;
+    double* h_scal = nullptr;  // pinned mirror for D2H of scalars
+    int* ring_flag = nullptr;
+    bool have_v = false, have_phi = false;
+    uint64_t launches = 0;
+    NcclComm comm = nullptr;
+    mutable std::string err;
+    size_t bytes() const { return (size_t)g.total() * sizeof(double); }
+};
+
+#define CK(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess) {                                                                        \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                             \
+            return WAFER_ERR_CUDA;                                                                      \
+        }                                                                                               \
+    } while (0)
+
+#define NK(call)                                                                                        \
+    do {                                                                                                \
+        int r_ = (call);                                                                                \
+        if (r_ != kNcclSuccess) {                                                                       \
+            ctx->err = std::string(#call) + ": " + nccl_api().GetErrorString(r_);                      \
+            return WAFER_ERR_NCCL;                                                                      \
+        }                                                                                               \
+    } while (0)
+
+#define REQUIRE(cond, msg)                                                                              \
+    do {                                                                                                \
+        if (!(cond)) {                                                                                  \
+            ctx->err = msg;                                                                             \
+            return WAFER_ERR_INVALID;                                                                   \
+        }                                                                                               \
+    } while (0)
+
+#define TRY(expr)                                                                                       \
+    do {                                                                                                \
+        int t_ = (expr);                                                                                \
+        if (t_ != WAFER_OK) return t_;                                                                  \
+    } while (0)
+
+namespace {
+
+inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+double denominator(const wafer_ctx* c) {
+    // grid.rs:569/594/626: r64(k)*dn*dn*mass, left to right
+    const double k = c->p.ext == 1 ? 2. : (c->p.ext == 2 ? 24. : 360.);
+    return k * c->p.dn * c->p.dn * c->p.mass;
+}
+
+int post_launch(wafer_ctx* ctx, int n = 1) {
+    ctx->launches += n;
+    CK(cudaGetLastError());
+    return WAFER_OK;
+}
+
+int ew_grid(const wafer_ctx* ctx, long long n2) {
+    return (int)std::min<long long>(ceil_div(n2, EW_THREADS), (long long)ctx->sm_count * 8);
+}
+
+// reduce `ns` rows of `nblocks` partials into scal[slot..slot+ns) and all-reduce across ranks
+int finalize(wafer_ctx* ctx, int ns, int nblocks, int slot, cudaStream_t st) {
+    if (ns == 1) finalize_kernel<1><<<1, 1024, 0, st>>>(ctx->partials, nblocks, ctx->scal + slot);
+    else finalize_kernel<4><<<1, 1024, 0, st>>>(ctx->partials, nblocks, ctx->scal + slot);
+    TRY(post_launch(ctx));
+    if (ctx->world > 1)
+        NK(nccl_api().AllReduce(ctx->scal + slot, ctx->scal + slot, ns, kNcclFloat64, kNcclSum, ctx->comm, st));
+    return WAFER_OK;
+}
+
+__global__ void set_scalar_kernel(double* p, double v) { *p = v; }
+
+// ---- sweep dispatch ------------------------------------------------------------------------------------
+template <int E>
+int launch_sweep_simple(wafer_ctx* ctx, const double* cur, double* nxt, int xb, int xe, bool norm, long long part_off,
+                        cudaStream_t st) {
+    const Geom& g = ctx->g;
+    if (xe <= xb) return WAFER_OK;
+    dim3 grid(ceil_div(g.nz, 2 * SW_BX), ceil_div(g.ny, SW_BY), ceil_div(xe - xb, SW_XCH)), block(SW_BX, SW_BY);
+    const double den = denominator(ctx), dt = ctx->p.dt;
+    double* part = ctx->partials + part_off;
+    const double* fa = ctx->onfly ? ctx->v : ctx->a;
+    const double* fb = ctx->b;
+    if (ctx->onfly) {
+        if (norm) sweep_simple_kernel<E, true, true><<<grid, block, 0, st>>>(cur, nxt, fa, fb, g, xb, xe, dt, den, part);
+        else sweep_simple_kernel<E, true, false><<<grid, block, 0, st>>>(cur, nxt, fa, fb, g, xb, xe, dt, den, part);
+    } else {
+        if (norm) sweep_simple_kernel<E, false, true><<<grid, block, 0, st>>>(cur, nxt, fa, fb, g, xb, xe, dt, den, part);
+        else sweep_simple_kernel<E, false, false><<<grid, block, 0, st>>>(cur, nxt, fa, fb, g, xb, xe, dt, den, part);
+    }
+    return post_launch(ctx);
+}
+
+int sweep_blocks(const wafer_ctx* ctx, int xb, int xe) {
+    const Geom& g = ctx->g;
+    return ceil_div(g.nz, 2 * SW_BX) * ceil_div(g.ny, SW_BY) * ceil_div(xe - xb, SW_XCH);
+}
+
+int launch_sweep(wafer_ctx* ctx, const double* cur, double* nxt, int xb, int xe, bool norm, long long part_off,
+                 cudaStream_t st) {
+    switch (ctx->p.ext) {
+        case 1: return launch_sweep_simple<1>(ctx, cur, nxt, xb, xe, norm, part_off, st);
+        case 2: return launch_sweep_simple<2>(ctx, cur, nxt, xb, xe, norm, part_off, st);
+        default: return launch_sweep_simple<3>(ctx, cur, nxt, xb, xe, norm, part_off, st);
+    }
+}
+
+// ghost-plane halo exchange of `buf` with the x neighbours (NCCL send/recv over NVLink)
+int exchange(wafer_ctx* ctx, double* buf, cudaStream_t st) {
+    if (ctx->world <= 1) return WAFER_OK;
+    const Geom& g = ctx->g;
+    const size_t cnt = (size_t)g.e * g.plane;
+    NcclApi& n = nccl_api();
+    NK(n.GroupStart());
+    if (ctx->rank > 0) {
+        NK(n.Send(buf + g.off(0, -g.e, 0), cnt, kNcclFloat64, ctx->rank - 1, ctx->comm, st));
+        NK(n.Recv(buf + g.off(-g.e, -g.e, 0), cnt, kNcclFloat64, ctx->rank - 1, ctx->comm, st));
+    }
+    if (ctx->rank < ctx->world - 1) {
+        NK(n.Send(buf + g.off(g.L - g.e, -g.e, 0), cnt, kNcclFloat64, ctx->rank + 1, ctx->comm, st));
+        NK(n.Recv(buf + g.off(g.L, -g.e, 0), cnt, kNcclFloat64, ctx->rank + 1, ctx->comm, st));
+    }
+    NK(n.GroupEnd());
+    return WAFER_OK;
+}
+
+// ---- Gram-Schmidt chain (grid.rs:477-492), optionally preceded by the normalise of grid.rs:465-468 -------
+// norm_slot < 0: no normalise.  Each pass fuses "psi -= q_{i-1} s_{i-1}" with the next overlap sum.
+template <bool N, bool A, bool D>
+int launch_gs(wafer_ctx* ctx, double* psi, int norm_slot, const double* qp, int sp_slot, const double* qn) {
+    const Geom& g = ctx->g;
+    const long long n2 = g.total() / 2;
+    const long long ob = (long long)g.gx * g.plane / 2, oe = (long long)(g.gx + g.L) * g.plane / 2;
+    const int grid = ew_grid(ctx, n2);
+    gs_pass_kernel<N, A, D><<<grid, EW_THREADS, 0, ctx->s_main>>>(
+        psi, n2, norm_slot >= 0 ? ctx->scal + norm_slot : nullptr, qp, sp_slot >= 0 ? ctx->scal + sp_slot : nullptr, qn,
+        ob, oe, ctx->partials);
+    return post_launch(ctx);
+}
+
+int gs_chain(wafer_ctx* ctx, int norm_slot, int wnum) {
+    double* psi = ctx->psi[ctx->cur];
+    const long long n2 = ctx->g.total() / 2;
+    const int grid = ew_grid(ctx, n2);
+    if (wnum == 0) {
+        if (norm_slot >= 0) TRY((launch_gs<true, false, false>(ctx, psi, norm_slot, nullptr, -1, nullptr)));
+        return WAFER_OK;
+    }
+    if (norm_slot >= 0) TRY((launch_gs<true, false, true>(ctx, psi, norm_slot, nullptr, -1, ctx->lowers[0])));
+    else TRY((launch_gs<false, false, true>(ctx, psi, -1, nullptr, -1, ctx->lowers[0])));
+    TRY(finalize(ctx, 1, grid, SL_DOT, ctx->s_main));
+    for (int i = 1; i < wnum; ++i) {
+        TRY((launch_gs<false, true, true>(ctx, psi, -1, ctx->lowers[i - 1], SL_DOT + i - 1, ctx->lowers[i])));
+        TRY(finalize(ctx, 1, grid, SL_DOT + i, ctx->s_main));
+    }
+    return launch_gs<false, true, false>(ctx, psi, -1, ctx->lowers[wnum - 1], SL_DOT + wnum - 1, nullptr);
+}
+
+int observables_device(wafer_ctx* ctx) {
+    const Geom& g = ctx->g;
+    dim3 grid(ceil_div(g.nz, SW_BX), ceil_div(g.ny, SW_BY), ceil_div(g.L, SW_XCH)), block(SW_BX, SW_BY);
+    const int nb = grid.x * grid.y * grid.z;
+    const double den = denominator(ctx);
+    const double* cur = ctx->psi[ctx->cur];
+#define OBS(E, M) observables_kernel<E, M><<<grid, block, 0, ctx->s_main>>>(cur, ctx->v, ctx->potsub_arr, ctx->potsub_scalar, g, den, ctx->partials)
+#define OBS_E(E)                                   \
+    if (ctx->potsub_mode == 0) OBS(E, 0);          \
+    else if (ctx->potsub_mode == 1) OBS(E, 1);     \
+    else OBS(E, 2);
+    if (ctx->p.ext == 1) { OBS_E(1) } else if (ctx->p.ext == 2) { OBS_E(2) } else { OBS_E(3) }
+#undef OBS_E
+#undef OBS
+    TRY(post_launch(ctx));
+    return finalize(ctx, 4, nb, SL_OBS, ctx->s_main);
+}
+
+int read_scalars(wafer_ctx* ctx, int slot, int n, double* out) {
+    CK(cudaMemcpyAsync(ctx->h_scal + slot, ctx->scal + slot, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->s_main));
+    CK(cudaStreamSynchronize(ctx->s_main));
+    for (int i = 0; i < n; ++i) out[i] = ctx->h_scal[slot + i];
+    return WAFER_OK;
+}
+
+// ---- host <-> device layout ------------------------------------------------------------------------------
+// planes of the reference's padded array held by this rank (owned + ghosts), clipped to the array
+void chunk_range(const wafer_ctx* ctx, bool worksized, long long* hp0, long long* hp1) {
+    const Geom& g = ctx->g;
+    const long long off = worksized ? 0 : g.e, top = worksized ? g.gnx : g.gnx + 2 * g.e;
+    *hp0 = std::max<long long>(0, g.x0 + off - g.gx);
+    *hp1 = std::min<long long>(top, g.x0 + g.L + off + g.gx);
+}
+
+void owned_range(const wafer_ctx* ctx, long long* hp0, long long* hp1) {
+    // planes this rank is responsible for in the caller's global array: owned, plus the outer ring at the ends
+    const Geom& g = ctx->g;
+    *hp0 = g.x0 + g.e;
+    *hp1 = g.x0 + g.L + g.e;
+    if (ctx->rank == 0) *hp0 = 0;
+    if (ctx->rank == ctx->world - 1) *hp1 = g.gnx + 2 * g.e;
+}
+
+// host_is_chunk: `host` already points at plane hp0 (the _slab entry points) instead of at the global array
+int upload(wafer_ctx* ctx, const double* host, double* dst, bool worksized, bool check_ring, bool host_is_chunk = false) {
+    const Geom& g = ctx->g;
+    long long hp0, hp1;
+    chunk_range(ctx, worksized, &hp0, &hp1);
+    const long long py = worksized ? g.ny : g.ny + 2 * g.e, pz = worksized ? g.nz : g.nz + 2 * g.e;
+    double* staging = ctx->psi[ctx->cur ^ 1];
+    if (dst == staging) { ctx->err = "internal: upload into the staging buffer"; return WAFER_ERR_INVALID; }
+    CK(cudaMemcpyAsync(staging, host + (host_is_chunk ? 0 : hp0 * py * pz), (size_t)((hp1 - hp0) * py * pz) * sizeof(double),
+                       cudaMemcpyHostToDevice, ctx->s_main));
+    if (check_ring) CK(cudaMemsetAsync(ctx->ring_flag, 0, sizeof(int), ctx->s_main));
+    const int grid = ctx->sm_count * 16;
+    if (check_ring) unpack_kernel<true><<<grid, 256, 0, ctx->s_main>>>(staging, dst, g, hp0, hp1, worksized ? 1 : 0, ctx->ring_flag);
+    else unpack_kernel<false><<<grid, 256, 0, ctx->s_main>>>(staging, dst, g, hp0, hp1, worksized ? 1 : 0, ctx->ring_flag);
+    TRY(post_launch(ctx));
+    if (check_ring) {
+        int flag = 0;
+        CK(cudaMemcpyAsync(&flag, ctx->ring_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->s_main));
+        CK(cudaStreamSynchronize(ctx->s_main));
+        if (flag) {
+            ctx->err = "padding ring of the wavefunction is not zero (config.rs:597-622 guarantees it)";
+            return WAFER_ERR_RING_NONZERO;
+        }
+    } else {
+        CK(cudaStreamSynchronize(ctx->s_main));  // the caller may free its buffer on return
+    }
+    return WAFER_OK;
+}
+
+int download(wafer_ctx* ctx, const double* src, double* host, bool host_is_chunk = false) {
+    const Geom& g = ctx->g;
+    long long hp0, hp1;
+    owned_range(ctx, &hp0, &hp1);
+    const long long py = g.ny + 2 * g.e, pz = g.nz + 2 * g.e;
+    double* staging = ctx->psi[ctx->cur ^ 1];
+    if (src == staging) { ctx->err = "internal: download from the staging buffer"; return WAFER_ERR_INVALID; }
+    pack_kernel<<<ctx->sm_count * 16, 256, 0, ctx->s_main>>>(src, staging, g, hp0, hp1, 0);
+    TRY(post_launch(ctx));
+    CK(cudaMemcpyAsync(host + (host_is_chunk ? 0 : hp0 * py * pz), staging, (size_t)((hp1 - hp0) * py * pz) * sizeof(double),
+                       cudaMemcpyDeviceToHost, ctx->s_main));
+    CK(cudaStreamSynchronize(ctx->s_main));
+    return WAFER_OK;
+}
+
+int alloc_field(wafer_ctx* ctx, double** p) {
+    CK(cudaMalloc(p, ctx->bytes()));
+    CK(cudaMemsetAsync(*p, 0, ctx->bytes(), ctx->s_main));
+    return WAFER_OK;
+}
+
+int ensure_ab(wafer_ctx* ctx) {
+    if (ctx->onfly) return WAFER_OK;
+    if (!ctx->a) TRY(alloc_field(ctx, &ctx->a));
+    if (!ctx->b) TRY(alloc_field(ctx, &ctx->b));
+    const long long n = ctx->g.total();
+    build_ab_kernel<<<ew_grid(ctx, n), EW_THREADS, 0, ctx->s_main>>>(ctx->v, ctx->a, ctx->b, n, ctx->p.dt);
+    return post_launch(ctx);
+}
+
+int create_impl(const wafer_params* params, wafer_ctx* ctx) {
+    const wafer_params& p = *params;
+    REQUIRE(p.nx > 0 && p.ny > 0 && p.nz > 0, "grid.size must be positive");
+    REQUIRE(p.ext >= 1 && p.ext <= 3, "ext must be 1 (ThreePoint), 2 (FivePoint) or 3 (SevenPoint)");
+    REQUIRE(p.nx < (1u << 30) && p.ny < (1u << 30) && p.nz < (1u << 30), "grid.size too large");
+    REQUIRE(std::isfinite(p.dn) && std::isfinite(p.dt) && std::isfinite(p.mass) && p.dn > 0 && p.mass != 0,
+            "dn, dt, mass must be finite (dn > 0, mass != 0)");
+    ctx->p = p;
+    ctx->p.nccl_id = nullptr;
+    ctx->world = p.world == 0 ? 1 : (int)p.world;
+    ctx->rank = (int)p.rank;
+    REQUIRE(ctx->rank < ctx->world, "rank must be < world");
+    ctx->onfly = !(p.flags & WAFER_FLAG_AB_ARRAYS);
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        ctx->err = "no CUDA device visible: this library has no CPU fallback";
+        return WAFER_ERR_NO_DEVICE;
+    }
+    int dev = p.device;
+    if (dev < 0) {
+        const char* lr = getenv("LOCAL_RANK");
+        dev = lr ? atoi(lr) % ndev : 0;
+    }
+    if (dev >= ndev) { ctx->err = "device ordinal out of range"; return WAFER_ERR_NO_DEVICE; }
+    ctx->dev = dev;
+    CK(cudaSetDevice(dev));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10) {
+        ctx->err = std::string("device '") + prop.name + "' is not sm_100 (Blackwell B200); this build targets sm_100a only";
+        return WAFER_ERR_NO_DEVICE;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+
+    // slab decomposition along x
+    Geom& g = ctx->g;
+    const long long base = p.nx / ctx->world, rem = p.nx % ctx->world;
+    g.L = (int)(base + (ctx->rank < rem ? 1 : 0));
+    g.x0 = ctx->rank * base + std::min<long long>(ctx->rank, rem);
+    g.ny = (int)p.ny; g.nz = (int)p.nz; g.e = (int)p.ext; g.gx = g.e;
+    g.yp = g.ny + 2 * g.e;
+    g.zp = (int)(((long long)g.nz + 2 * g.e + 15) / 16 * 16);
+    g.plane = (long long)g.yp * g.zp;
+    g.gnx = p.nx; g.gny = p.ny; g.gnz = p.nz;
+    REQUIRE(ctx->world == 1 || g.L >= g.gx, "every rank needs at least `ext` planes of the lattice");
+
+    int lo, hi;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CK(cudaStreamCreateWithPriority(&ctx->s_main, cudaStreamNonBlocking, lo));
+    CK(cudaStreamCreateWithPriority(&ctx->s_halo, cudaStreamNonBlocking, hi));
+    CK(cudaEventCreate(&ctx->ev_t0));
+    CK(cudaEventCreate(&ctx->ev_t1));
+    CK(cudaEventCreateWithFlags(&ctx->ev_main, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->ev_halo, cudaEventDisableTiming));
+
+    TRY(alloc_field(ctx, &ctx->psi[0]));
+    TRY(alloc_field(ctx, &ctx->psi[1]));
+    TRY(alloc_field(ctx, &ctx->v));
+    const long long nb = std::max<long long>(
+        {(long long)sweep_blocks(ctx, 0, g.L) + 4 * sweep_blocks(ctx, 0, g.e),
+         (long long)ceil_div(g.nz, SW_BX) * ceil_div(g.ny, SW_BY) * ceil_div(g.L, SW_XCH), (long long)ctx->sm_count * 8});
+    ctx->partials_cap = nb * 4;
+    CK(cudaMalloc(&ctx->partials, ctx->partials_cap * sizeof(double)));
+    CK(cudaMalloc(&ctx->scal, SL_COUNT * sizeof(double)));
+    CK(cudaMemsetAsync(ctx->scal, 0, SL_COUNT * sizeof(double), ctx->s_main));
+    CK(cudaMallocHost(&ctx->h_scal, SL_COUNT * sizeof(double)));
+    CK(cudaMalloc(&ctx->ring_flag, sizeof(int)));
+
+    if (ctx->world > 1) {
+        if (!p.nccl_id) { ctx->err = "world > 1 needs the 128-byte nccl_id of rank 0"; return WAFER_ERR_INVALID; }
+        if (const char* why = nccl_api().load()) { ctx->err = why; return WAFER_ERR_NCCL; }
+        NcclUniqueId id;
+        memcpy(id.internal, p.nccl_id, sizeof(id.internal));
+        NK(nccl_api().CommInitRank(&ctx->comm, ctx->world, id, ctx->rank));
+    }
+    CK(cudaStreamSynchronize(ctx->s_main));
+    return WAFER_OK;
+}
+
+}  // namespace
+
+// =============================================================================================================
+extern "C" {
+
+const char* wafer_version(void) { return "wafer_b200 0.1 (sm_100a)"; }
+
+int wafer_create(const wafer_params* params, wafer_ctx** out) {
+    if (!params || !out) { g_create_error = "NULL argument"; return WAFER_ERR_INVALID; }
+    *out = nullptr;
+    wafer_ctx* ctx = new wafer_ctx();
+    const int rc = create_impl(params, ctx);
+    if (rc != WAFER_OK) {
+        g_create_error = ctx->err;
+        wafer_destroy(ctx);
+        return rc;
+    }
+    *out = ctx;
+    return WAFER_OK;
+}
+
+int wafer_destroy(wafer_ctx* ctx) {
+    if (!ctx) return WAFER_OK;
+    if (ctx->s_main) cudaStreamSynchronize(ctx->s_main);
+    if (ctx->s_halo) cudaStreamSynchronize(ctx->s_halo);
+    if (ctx->comm) nccl_api().CommDestroy(ctx->comm);
+    for (double* q : ctx->lowers) cudaFree(q);
+    cudaFree(ctx->psi[0]); cudaFree(ctx->psi[1]); cudaFree(ctx->v); cudaFree(ctx->a); cudaFree(ctx->b);
+    cudaFree(ctx->potsub_arr); cudaFree(ctx->partials); cudaFree(ctx->scal); cudaFree(ctx->ring_flag);
+    if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
+    if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
+    if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
+    if (ctx->ev_main) cudaEventDestroy(ctx->ev_main);
+    if (ctx->ev_halo) cudaEventDestroy(ctx->ev_halo);
+    if (ctx->s_main) cudaStreamDestroy(ctx->s_main);
+    if (ctx->s_halo) cudaStreamDestroy(ctx->s_halo);
+    delete ctx;
+    return WAFER_OK;
+}
+
+const char* wafer_last_error(const wafer_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int wafer_nccl_unique_id(uint8_t out[128]) {
+    if (!out) return WAFER_ERR_INVALID;
+    if (const char* why = nccl_api().load()) { g_create_error = why; return WAFER_ERR_NCCL; }
+    NcclUniqueId id;
+    if (nccl_api().GetUniqueId(&id) != kNcclSuccess) { g_create_error = "ncclGetUniqueId failed"; return WAFER_ERR_NCCL; }
+    memcpy(out, id.internal, 128);
+    return WAFER_OK;
+}
+
+int wafer_slab(const wafer_ctx* ctx, uint64_t* x0, uint64_t* x1) {
+    if (!ctx) return WAFER_ERR_INVALID;
+    if (x0) *x0 = (uint64_t)ctx->g.x0;
+    if (x1) *x1 = (uint64_t)(ctx->g.x0 + ctx->g.L);
+    return WAFER_OK;
+}
+
+// ---- state in / out ------------------------------------------------------------------------------------------
+int wafer_set_potential(wafer_ctx* ctx, const double* v_padded) {
+    if (!ctx) return WAFER_ERR_INVALID;
+    REQUIRE(v_padded, "v_padded is NULL");
+    CK(cudaSetDevice(ctx->dev));
+    TRY(upload(ctx, v_padded, ctx->v, false, false));
+    TRY(ensure_ab(ctx));
+    ctx->have_v = true;
+    return WAFER_OK;
+}
+
+int wafer_get_potential(wafer_ctx* ctx, double* v_padded) {
+    if (!ctx) return WAFER_ERR_INVALID;
+    REQUIRE(v_padded, "v_padded is NULL");
+    if (!ctx->have_v) { ctx->err = "potential not set"; return WAFER_ERR_NOT_READY; }
+    CK(cudaSetDevice(ctx->dev));
+    return download(ctx, ctx->v, v_padded);
+}
+
+int wafer_set_pot_sub_scalar(wafer_ctx* ctx, double c) {
+    if (!ctx) return WAFER_ERR_INVALID;
+    // potential.rs:148-152: (None, Some(c)) only when c > 0, else (None, None)
+    ctx->potsub_mode = c > 0.0 ? 1 : 0;
+    ctx->potsub_scalar = c > 0.0 ? c : 0.0;
+    return WAFER_OK;
+}
+
+int wafer_set_pot_sub_array(wafer_ctx* ctx, const double* work) {
+    if (!ctx) return WAFER_ERR_INVALID;
+    REQUIRE(work, "pot_sub array is NULL");
+    CK(cudaSetDevice(ctx->dev));
+    if (!ctx->potsub_arr) TRY(alloc_field(ctx, &ctx->potsub_arr));
+    TRY(upload(ctx, work, ctx->potsub_arr, true, false));
+    ctx->potsub_mode = 2;
+    return WAFER_OK;
+}
+
+int wafer_set_phi(wafer_ctx* ctx, const double* phi_padded) {
+    if (!ctx) return WAFER_ERR_INVALID;
+    REQUIRE(phi_padded, "phi_padded is NULL");
+    CK(cudaSetDevice(ctx->dev));
+    const int rc = upload(ctx, phi_padded, ctx->psi[ctx->cur], false, true);
+    ctx->have_phi = rc == WAFER_OK;
+    return rc;
+}
+
+int wafer_get_phi(wafer_ctx* ctx, double* phi_padded) {
+    if (!ctx) return WAFER_ERR_INVALID;
+    REQUIRE(phi_padded, "phi_padded is NULL");
+    if (!ctx->have_phi) { ctx->err = "phi not set"; return WAFER_ERR_NOT_READY; }
+    CK(cudaSetDevice(ctx->dev));
+    return download(ctx, ctx->psi[ctx->cur], phi_padded);
+}
+
+int wafer_slab_planes(const wafer_ctx* ctx, int32_t which, uint64_t* p0, uint64_t* p1) {
+    if (!ctx) return WAFER_ERR_INVALID;
+    long long a, b;
+    if (which == 0) chunk_range(ctx, false, &a, &b);
+    else owned_range(ctx, &a, &b);
+    if (p0) *p0 = (uint64_t)a;
+    if (p1) *p1 = (uint64_t)b;
+    return WAFER_OK;
+}
+
+int wafer_set_phi_slab(wafer_ctx* ctx, const double* chunk) {
+    if (!ctx) return WAFER_ERR_INVALID;
+    REQUIRE(chunk, "chunk is NULL");
+    CK(cudaSetDevice(ctx->dev));
+    const int rc = upload(ctx, chunk, ctx->psi[ctx->cur], false, true, true);
+    ctx->have_phi = rc == WAFER_OK;
+    return rc;
+}
+
+int wafer_get_phi_slab(wafer_ctx* ctx, double* chunk) {
+    if (!ctx) return WAFER_ERR_INVALID;
+    REQUIRE(chunk, "chunk is NULL");
+    if (!ctx->have_phi) { ctx->err = "phi not set"; return WAFER_ERR_NOT_READY; }
+    CK(cudaSetDevice(ctx->dev));
+    return download(ctx, ctx->psi[ctx->cur], chunk, true);
+}
+
+int wafer_push_lower(wafer_ctx* ctx, const double* q_padded) {
+    if (!ctx) return WAFER_ERR_INVALID;
+    REQUIRE(q_padded, "q_padded is NULL");
+    REQUIRE(ctx->lowers.size() < 255, "at most 255 lower states (wavenum is a u8, config.rs:308)");
+    CK(cudaSetDevice(ctx->dev));
+    double* q = nullptr;
+    TRY(alloc_field(ctx, &q));
+    const int rc = upload(ctx, q_padded, q, false, true);
+    if (rc != WAFER_OK) { cudaFree(q); return rc; }
+    ctx->lowers.push_back(q);
+    return WAFER_OK;
+}
+
+int wafer_push_lower_from_phi(wafer_ctx* ctx) {
+    if (!ctx) return WAFER_ERR_INVALID;
+    if (!ctx->have_phi) { ctx->err = "phi not set"; return WAFER_ERR_NOT_READY; }
+    REQUIRE(ctx->lowers.size() < 255, "at most 255 lower states (wavenum is a u8, config.rs:308)");
+    CK(cudaSetDevice(ctx->dev));
+    double* q = nullptr;
+    CK(cudaMalloc(&q, ctx->bytes()));
+    CK(cudaMemcpyAsync(q, ctx->psi[ctx->cur], ctx->bytes(), cudaMemcpyDeviceToDevice, ctx->s_main));
+    ctx->lowers.push_back(q);
+    return WAFER_OK;
+}
+
+int wafer_get_lower(wafer_ctx* ctx, uint32_t idx, double* q_padded) {
+    if (!ctx) return WAFER_ERR_INVALID;
+    REQUIRE(q_padded && idx < ctx->lowers.size(), "no such lower state");
+    CK(cudaSetDevice(ctx->dev));
+    return download(ctx, ctx->lowers[idx], q_padded);
+}
+
+int wafer_phi_from_lower(wafer_ctx* ctx, uint32_t idx) {
+    if (!ctx) return WAFER_ERR_INVALID;
+    REQUIRE(idx < ctx->lowers.size(), "no such lower state");
+    CK(cudaSetDevice(ctx->dev));
+    CK(cudaMemcpyAsync(ctx->psi[ctx->cur], ctx->lowers[idx], ctx->bytes(), cudaMemcpyDeviceToDevice, ctx->s_main));
+    ctx->have_phi = true;
+    return WAFER_OK;
+}
+
+int wafer_clear_lowers(wafer_ctx* ctx) {
+    if (!ctx) return WAFER_ERR_INVALID;
+    CK(cudaSetDevice(ctx->dev));
+    CK(cudaStreamSynchronize(ctx->s_main));
+    for (double* q : ctx->lowers) cudaFree(q);
+    ctx->lowers.clear();
+    return WAFER_OK;
+}
+
+uint32_t wafer_num_lowers(const wafer_ctx* ctx) { return ctx ? (uint32_t)ctx->lowers.size() : 0; }
+
+int wafer_generate_potential(wafer_ctx* ctx, int32_t kind, double sig) {
+    if (!ctx) return WAFER_ERR_INVALID;
+    CK(cudaSetDevice(ctx->dev));
+    GenParams gp = make_gen_params(ctx->p.dn, ctx->p.mass, sig);
+    REQUIRE(potential_kind_supported(kind), "PotentialNotAvailable: no formula for this potential kind (potential.rs:315-317)");
+    const long long rows = (long long)(ctx->g.L + 2 * ctx->g.gx) * ctx->g.ny;
+    gen_potential_kernel<<<(int)std::min<long long>(rows, (long long)ctx->sm_count * 32), 128, 0, ctx->s_main>>>(ctx->v, ctx->g, kind, gp);
+    TRY(post_launch(ctx));
+    TRY(ensure_ab(ctx));
+    ctx->have_v = true;
+    return WAFER_OK;
+}
+
+int wafer_generate_initial_condition(wafer_ctx* ctx, int32_t kind) {
+    if (!ctx) return WAFER_ERR_INVALID;
+    REQUIRE(kind >= 2 && kind <= 4, "only Coulomb (2), Constant (3) and Boolean (4) can be generated on the device");
+    CK(cudaSetDevice(ctx->dev));
+    GenParams gp = make_gen_params(ctx->p.dn, ctx->p.mass, 0.0);
+    const long long rows = (long long)(ctx->g.L + 2 * ctx->g.gx) * ctx->g.ny;
+    gen_ic_kernel<<<(int)std::min<long long>(rows, (long long)ctx->sm_count * 32), 128, 0, ctx->s_main>>>(ctx->psi[ctx->cur], ctx->g, kind, gp);
+    TRY(post_launch(ctx));
+    ctx->have_phi = true;
+    return WAFER_OK;
+}
+
+// ---- the hot path --------------------------------------------------------------------------------------------
+static int ready(wafer_ctx* ctx, bool need_v) {
+    if (!ctx->have_phi) { ctx->err = "phi not set (wafer_set_phi / wafer_generate_initial_condition)"; return WAFER_ERR_NOT_READY; }
+    if (need_v && !ctx->have_v) { ctx->err = "potential not set (wafer_set_potential / wafer_generate_potential)"; return WAFER_ERR_NOT_READY; }
+    return WAFER_OK;
+}
+
+int wafer_observables_compute(wafer_ctx* ctx, wafer_observables* out) {
+    if (!ctx) return WAFER_ERR_INVALID;
+    REQUIRE(out, "out is NULL");
+    TRY(ready(ctx, true));
+    CK(cudaSetDevice(ctx->dev));
+    TRY(observables_device(ctx));
+    double s[4];
+    TRY(read_scalars(ctx, SL_OBS, 4, s));
+    out->energy = s[0]; out->norm2 = s[1]; out->v_infinity = s[2]; out->r2 = s[3];
+    return WAFER_OK;
+}
+
+int wafer_norm2(wafer_ctx* ctx, double* out) {
+    if (!ctx) return WAFER_ERR_INVALID;
+    REQUIRE(out, "out is NULL");
+    TRY(ready(ctx, false));
+    CK(cudaSetDevice(ctx->dev));
+    const Geom& g = ctx->g;
+    const long long ob = (long long)g.gx * g.plane / 2, oe = (long long)(g.gx + g.L) * g.plane / 2;
+    const int grid = ew_grid(ctx, oe - ob);
+    norm2_kernel<<<grid, EW_THREADS, 0, ctx->s_main>>>(ctx->psi[ctx->cur], ob, oe, ctx->partials);
+    TRY(post_launch(ctx));
+    TRY(finalize(ctx, 1, grid, SL_TMP, ctx->s_main));
+    return read_scalars(ctx, SL_TMP, 1, out);
+}
+
+int wafer_normalise(wafer_ctx* ctx, double norm2) {
+    if (!ctx) return WAFER_ERR_INVALID;
+    TRY(ready(ctx, false));
+    CK(cudaSetDevice(ctx->dev));
+    set_scalar_kernel<<<1, 1, 0, ctx->s_main>>>(ctx->scal + SL_TMP, norm2);
+    TRY(post_launch(ctx));
+    return gs_chain(ctx, SL_TMP, 0);
+}
+
+int wafer_orthogonalise(wafer_ctx* ctx, uint8_t wnum) {
+    if (!ctx) return WAFER_ERR_INVALID;
+    TRY(ready(ctx, false));
+    // grid.rs:478: w_store.iter().take(wnum) — silently clamps to the stored count
+    const int n = std::min<int>(wnum, (int)ctx->lowers.size());
+    if (n == 0) return WAFER_OK;
+    CK(cudaSetDevice(ctx->dev));
+    return gs_chain(ctx, -1, n);
+}
+
+int wafer_evolve(wafer_ctx* ctx, uint8_t wnum_in, uint64_t steps) {
+    if (!ctx) return WAFER_ERR_INVALID;
+    TRY(ready(ctx, true));
+    CK(cudaSetDevice(ctx->dev));
+    const Geom& g = ctx->g;
+    const int wnum = std::min<int>(wnum_in, (int)ctx->lowers.size());
+    const bool excited = wnum_in > 0;  // grid.rs:674: norm/normalise run for wnum > 0 even with an empty w_store
+    const bool overlap = ctx->world > 1 && !excited && g.L > 2 * g.e;
+    if (overlap) {
+        CK(cudaEventRecord(ctx->ev_main, ctx->s_main));
+        CK(cudaEventRecord(ctx->ev_halo, ctx->s_main));
+    }
+    uint64_t done = 0;
+    do {  // grid.rs:562-686 is a do-while: steps == 0 still performs one sweep
+        const double* cur = ctx->psi[ctx->cur];
+        double* nxt = ctx->psi[ctx->cur ^ 1];
+        if (overlap) {
+            // boundary planes + NVLink halo exchange on the high-priority stream, interior on the main stream
+            CK(cudaStreamWaitEvent(ctx->s_halo, ctx->ev_main, 0));
+            CK(cudaStreamWaitEvent(ctx->s_main, ctx->ev_halo, 0));
+            TRY(launch_sweep(ctx, cur, nxt, 0, g.e, false, 0, ctx->s_halo));
+            TRY(launch_sweep(ctx, cur, nxt, g.L - g.e, g.L, false, 0, ctx->s_halo));
+            TRY(exchange(ctx, nxt, ctx->s_halo));
+            CK(cudaEventRecord(ctx->ev_halo, ctx->s_halo));
+            TRY(launch_sweep(ctx, cur, nxt, g.e, g.L - g.e, false, 0, ctx->s_main));
+            CK(cudaEventRecord(ctx->ev_main, ctx->s_main));
+        } else {
+            TRY(launch_sweep(ctx, cur, nxt, 0, g.L, excited, 0, ctx->s_main));
+            TRY(exchange(ctx, nxt, ctx->s_main));
+        }
+        ctx->cur ^= 1;
+        if (excited) {
+            TRY(finalize(ctx, 1, sweep_blocks(ctx, 0, g.L), SL_NORM, ctx->s_main));
+            TRY(gs_chain(ctx, SL_NORM, wnum));
+        }
+        done += 1;
+    } while (done < steps);
+    if (overlap) CK(cudaStreamWaitEvent(ctx->s_main, ctx->ev_halo, 0));
+    return WAFER_OK;
+}
+
+int wafer_check(wafer_ctx* ctx, uint8_t wnum_in, wafer_observables* out) {
+    if (!ctx) return WAFER_ERR_INVALID;
+    REQUIRE(out, "out is NULL");
+    TRY(ready(ctx, true));
+    CK(cudaSetDevice(ctx->dev));
+    const int wnum = std::min<int>(wnum_in, (int)ctx->lowers.size());
+    TRY(observables_device(ctx));                // grid.rs:127
+    TRY(gs_chain(ctx, SL_OBS + 1, wnum));        // grid.rs:130 normalise(norm2) then 133-135 orthogonalise
+    double s[4];
+    TRY(read_scalars(ctx, SL_OBS, 4, s));
+    out->energy = s[0]; out->norm2 = s[1]; out->v_infinity = s[2]; out->r2 = s[3];
+    return WAFER_OK;
+}
+
+// grid.rs:50-246
+int wafer_solve(wafer_ctx* ctx, uint8_t wnum, double tolerance, int64_t max_steps, uint64_t screen_update,
+                uint64_t snap_update, wafer_record* records, uint64_t max_records, uint64_t* n_records) {
+    if (!ctx) return WAFER_ERR_INVALID;
+    TRY(ready(ctx, true));
+    uint64_t step = 0, nrec = 0;
+    double last_energy = 1.7976931348623157e308;  // f64::MAX (grid.rs:124)
+    bool converged = false;
+    for (;;) {
+        wafer_observables obs;
+        TRY(wafer_check(ctx, wnum, &obs));                                  // grid.rs:127-135
+        if (!std::isfinite(obs.energy) || !std::isfinite(obs.norm2) || obs.norm2 == 0.0) {
+            ctx->err = "non-finite observables (the reference's R64 would panic here)";
+            return WAFER_ERR_NONFINITE;
+        }
+        const double norm_energy = obs.energy / obs.norm2;                  // grid.rs:128
+        const double tau = (double)step * ctx->p.dt;                        // grid.rs:129
+        if (snap_update != 0 && step % snap_update == 0)                    // grid.rs:137-139 (NotConstrained):
+            TRY(wafer_normalise(ctx, obs.norm2));                           // second division by sqrt(norm2)
+        const double diff = std::fabs(norm_energy - last_energy);           // grid.rs:161
+        if (records && nrec < max_records) {
+            records[nrec].step = step; records[nrec].tau = tau; records[nrec].diff = diff; records[nrec].obs = obs;
+        }
+        nrec++;
+        if (diff < tolerance) { converged = true; break; }                  // grid.rs:162-192
+        last_energy = norm_energy;                                          // grid.rs:194
+        if (max_steps >= 0 && step > (uint64_t)max_steps) break;            // grid.rs:211-213 (strict >)
+        TRY(wafer_evolve(ctx, wnum, screen_update));                        // grid.rs:216
+        step += screen_update;                                              // grid.rs:220
+    }
+    if (n_records) *n_records = nrec;
+    if (converged) {
+        TRY(wafer_push_lower_from_phi(ctx));                                // grid.rs:241
+        return WAFER_OK;
+    }
+    ctx->err = "Maximum step limit reached before convergence (ErrorKind::MaxStep)";
+    return WAFER_ERR_MAX_STEP;
+}
+
+// ---- plumbing ----------------------------------------------------------------------------------------------
+int wafer_synchronize(wafer_ctx* ctx) {
+    if (!ctx) return WAFER_ERR_INVALID;
+    CK(cudaSetDevice(ctx->dev));
+    CK(cudaStreamSynchronize(ctx->s_halo));
+    CK(cudaStreamSynchronize(ctx->s_main));
+    return WAFER_OK;
+}
+
+int wafer_timer_begin(wafer_ctx* ctx) {
+    if (!ctx) return WAFER_ERR_INVALID;
+    CK(cudaSetDevice(ctx->dev));
+    CK(cudaEventRecord(ctx->ev_t0, ctx->s_main));
+    return WAFER_OK;
+}
+
+int wafer_timer_end(wafer_ctx* ctx, double* ms) {
+    if (!ctx) return WAFER_ERR_INVALID;
+    REQUIRE(ms, "ms is NULL");
+    CK(cudaSetDevice(ctx->dev));
+    CK(cudaEventRecord(ctx->ev_t1, ctx->s_main));
+    CK(cudaEventSynchronize(ctx->ev_t1));
+    float f = 0.f;
+    CK(cudaEventElapsedTime(&f, ctx->ev_t0, ctx->ev_t1));
+    *ms = (double)f;
+    return WAFER_OK;
+}
+
+uint64_t wafer_kernel_launches(const wafer_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int wafer_host_alloc(void** ptr, size_t bytes) {
+    if (!ptr) return WAFER_ERR_INVALID;
+    return cudaMallocHost(ptr, bytes) == cudaSuccess ? WAFER_OK : WAFER_ERR_CUDA;
+}
+
+int wafer_host_free(void* ptr) { return cudaFreeHost(ptr) == cudaSuccess ? WAFER_OK : WAFER_ERR_CUDA; }
+
+int wafer_device_info(const wafer_ctx* ctx, char* name, size_t name_len, int32_t* sm_count, int32_t* cc_major,
+                      int32_t* cc_minor, uint64_t* mem_bytes) {
+    if (!ctx) return WAFER_ERR_INVALID;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, ctx->dev) != cudaSuccess) return WAFER_ERR_CUDA;
+    if (name && name_len) { strncpy(name, prop.name, name_len - 1); name[name_len - 1] = 0; }
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    if (mem_bytes) *mem_bytes = prop.totalGlobalMem;
+    return WAFER_OK;
+}
+
+const char* wafer_sweep_variant(const wafer_ctx* ctx) {
+    if (!ctx) return "";
+    return ctx->onfly ? "simple-regqueue/V-onfly" : "simple-regqueue/AB-arrays";
+}
+
+}  // extern "C"
