@@ -75,6 +75,9 @@ int wafer_destroy(wafer_ctx *ctx);
 const char *wafer_last_error(const wafer_ctx *ctx);     /* ctx may be NULL: message of the last failed wafer_create */
 int wafer_nccl_unique_id(uint8_t out[128]);             /* rank 0 calls this and ships the bytes to the other ranks  */
 int wafer_slab(const wafer_ctx *ctx, uint64_t *x0, uint64_t *x1); /* this rank's work planes [x0,x1)               */
+/* The decomposition rule itself (pure host arithmetic, no GPU needed): contiguous x-slabs, the first nx % world
+   ranks own one plane more.  wafer_create uses exactly this. */
+int wafer_slab_partition(uint64_t nx, uint32_t world, uint32_t rank, uint64_t *x0, uint64_t *x1);
 
 /* -------- state in / out ------------------------------------------------------------------------ */
 /* Potentials{v,a,b} (potential.rs:14-25): uploads V and builds b = 1/(1+dt*v/2), a = (1-dt*v/2)*b

@@ -1,0 +1,155 @@
+"""World-size-2 (and 3) CPU runs over gloo of the x-slab decomposition protocol the CUDA library uses for N > 1
+(wafer_b200.cu: wafer_slab_partition, exchange(), owned-plane reductions, element-wise passes over ghost planes).
+
+Each rank holds planes [x0-e, x1+e) of every field, sweeps its owned planes with the numpy restatement of the
+reference sweep, swaps `e` boundary planes with its neighbours after every sweep and all-reduces partial sums.
+The result must equal the single-domain run: bit-for-bit for the sweep, to rounding for the sums."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _exchange(dist, torch, loc, e, rank, world):
+    """ghost-plane swap of wafer_b200.cu::exchange: send owned boundary planes, receive into ghost planes"""
+    reqs, bufs = [], []
+    L = loc.shape[0] - 2 * e
+    if rank > 0:
+        s = torch.from_numpy(np.ascontiguousarray(loc[e:2 * e]))
+        r = torch.empty_like(s)
+        reqs += [dist.isend(s, rank - 1), dist.irecv(r, rank - 1)]
+        bufs.append((slice(0, e), r))
+    if rank < world - 1:
+        s = torch.from_numpy(np.ascontiguousarray(loc[L:L + e]))
+        r = torch.empty_like(s)
+        reqs += [dist.isend(s, rank + 1), dist.irecv(r, rank + 1)]
+        bufs.append((slice(L + e, L + 2 * e), r))
+    for q in reqs:
+        q.wait()
+    for sl, r in bufs:
+        loc[sl] = r.numpy()
+
+
+def _worker(rank, world, port, ext, shape, steps, nlow, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+
+    import np_restatement as npr
+    import wafer_b200
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    e, (nx, ny, nz) = ext, shape
+    dn, dt, mass = 0.1, 2e-3, 1.0
+    rng = np.random.default_rng(5)  # same global fields on every rank
+    P = (nx + 2 * e, ny + 2 * e, nz + 2 * e)
+    v = rng.normal(size=P)
+    phi = np.zeros(P)
+    npr.work(phi, e)[...] = rng.normal(size=shape)
+    lowers = []
+    for _ in range(nlow):
+        q = np.zeros(P)
+        npr.work(q, e)[...] = rng.normal(size=shape)
+        lowers.append(q / np.sqrt((q * q).sum()))
+    a, b = npr.build_ab(v, dt)
+    x0, x1 = wafer_b200.slab_partition(nx, world, rank)
+    sl = slice(x0, x1 + 2 * e)  # padded planes [x0, x1+2e) = owned + e ghosts each side
+    loc, la, lb, lv = phi[sl].copy(), a[sl], b[sl], v[sl]
+    llow = [q[sl].copy() for q in lowers]
+    own = slice(e, e + (x1 - x0))
+    for _ in range(steps):
+        loc = npr.sweep(loc, la, lb, e, dn, dt, mass)  # writes planes [e, L+e) only: exactly the owned planes
+        _exchange(dist, torch, loc, e, rank, world)
+        if nlow:
+            n2 = torch.tensor([float((npr.work(loc, e) ** 2).astype(np.longdouble).sum())], dtype=torch.float64)
+            dist.all_reduce(n2)
+            loc = loc / np.sqrt(n2.item())  # element-wise over ghosts too: no exchange needed afterwards
+            for q in llow:
+                s = torch.tensor([float((q[own] * loc[own]).astype(np.longdouble).sum())], dtype=torch.float64)
+                dist.all_reduce(s)
+                loc = loc - q * s.item()
+    # observables with GLOBAL work indices for r2 (grid.rs:432-433) on owned planes
+    den = npr.denominator(e, dn, mass)
+    w = npr.work(loc, e)
+    integrand = npr.work(lv, e) * w * w - w * npr.lap_sum(loc, e) / den
+    r2 = npr.calculate_r2_grid(shape)[x0:x1]
+    part = torch.tensor([float(integrand.astype(np.longdouble).sum()), float((w * w).astype(np.longdouble).sum()),
+                         float((w * w * r2).astype(np.longdouble).sum())], dtype=torch.float64)
+    dist.all_reduce(part)
+    np.save(os.path.join(out_dir, "slab_%d.npy" % rank), loc)
+    if rank == 0:
+        np.save(os.path.join(out_dir, "obs.npy"), part.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,ext,shape,nlow", [(2, 1, (10, 6, 7), 0), (2, 2, (9, 6, 8), 0), (3, 3, (11, 8, 8), 0),
+                                                   (2, 1, (8, 6, 6), 2)])
+def test_slab_decomposition_matches_single_domain(tmp_path, world, ext, shape, nlow):
+    import torch.multiprocessing as mp
+
+    import np_restatement as npr
+    import wafer_b200
+
+    steps = 4
+    port = 29500 + (os.getpid() + 7 * world + ext) % 2000
+    mp.spawn(_worker, args=(world, port, ext, shape, steps, nlow, str(tmp_path)), nprocs=world, join=True)
+
+    e, (nx, ny, nz) = ext, shape
+    dn, dt, mass = 0.1, 2e-3, 1.0
+    rng = np.random.default_rng(5)
+    P = (nx + 2 * e, ny + 2 * e, nz + 2 * e)
+    v = rng.normal(size=P)
+    phi = np.zeros(P)
+    npr.work(phi, e)[...] = rng.normal(size=shape)
+    lowers = []
+    for _ in range(nlow):
+        q = np.zeros(P)
+        npr.work(q, e)[...] = rng.normal(size=shape)
+        lowers.append(q / np.sqrt((q * q).sum()))
+    a, b = npr.build_ab(v, dt)
+    for _ in range(steps):
+        phi = npr.sweep(phi, a, b, e, dn, dt, mass)
+        if nlow:
+            n2 = float((npr.work(phi, e) ** 2).astype(np.longdouble).sum())
+            phi = npr.orthogonalise(npr.normalise(phi, n2), lowers)
+    got = np.zeros(P)
+    covered = 0
+    for r in range(world):
+        x0, x1 = wafer_b200.slab_partition(nx, world, r)
+        loc = np.load(tmp_path / ("slab_%d.npy" % r))
+        assert loc.shape[0] == x1 - x0 + 2 * e
+        got[x0 + e:x1 + e] = loc[e:e + x1 - x0]
+        # ghost planes hold the neighbour's boundary planes (or the zero ring at the ends)
+        assert np.array_equal(loc[:e], phi[x0:x0 + e]) if nlow == 0 else np.allclose(loc[:e], phi[x0:x0 + e], atol=1e-14)
+        covered += x1 - x0
+    assert covered == nx
+    if nlow == 0:
+        assert np.array_equal(got, phi)  # the sweep has no reductions: bit-identical to the single domain
+    else:
+        assert np.linalg.norm(got - phi) / np.linalg.norm(phi) < 1e-14
+    ref = npr.observables(phi, v, e, dn, mass)
+    obs = np.load(tmp_path / "obs.npy")
+    for val, key in zip(obs, ("energy", "norm2", "r2")):
+        assert val == pytest.approx(ref[key], rel=1e-12)
+
+
+def test_partition_rule():
+    import wafer_b200
+    for nx in (1, 7, 50, 1024, 2048):
+        for world in (1, 2, 3, 4, 8):
+            if world > nx:
+                continue
+            edges = [wafer_b200.slab_partition(nx, world, r) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == nx
+            assert all(edges[i][1] == edges[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in edges]
+            assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
+    with pytest.raises(wafer_b200.WaferError):
+        wafer_b200.slab_partition(8, 2, 2)

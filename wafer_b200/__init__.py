@@ -12,7 +12,7 @@ import numpy as np
 from . import _capi
 from ._capi import Observables, Params, Record
 
-__all__ = ["Lattice", "WaferError", "POTENTIALS", "INITIAL_CONDITIONS", "EXT", "nccl_unique_id", "pinned_empty",
+__all__ = ["Lattice", "slab_partition", "WaferError", "POTENTIALS", "INITIAL_CONDITIONS", "EXT", "nccl_unique_id", "pinned_empty",
            "FLAG_AB_ARRAYS"]
 
 # PotentialType (config.rs:74-104), InitialCondition (config.rs:153-170), CentralDifference.ext() (config.rs:232-238)
@@ -37,6 +37,15 @@ class WaferError(RuntimeError):
         self.status = status
 
 
+def slab_partition(nx, world, rank):
+    """work x-planes [x0, x1) owned by `rank` of `world` (wafer_slab_partition; pure host arithmetic)"""
+    x0, x1 = C.c_uint64(), C.c_uint64()
+    rc = _capi.load().wafer_slab_partition(nx, world, rank, C.byref(x0), C.byref(x1))
+    if rc:
+        raise WaferError(rc, "wafer_slab_partition(%d, %d, %d)" % (nx, world, rank))
+    return x0.value, x1.value
+
+
 def nccl_unique_id():
     """128-byte ncclUniqueId; rank 0 makes it, the harness broadcasts it (torch.distributed / MPI / a file)."""
     buf = (C.c_uint8 * 128)()
@@ -56,12 +65,16 @@ def pinned_empty(shape):
         raise WaferError(rc, "wafer_host_alloc(%d bytes) failed" % (n * 8))
     buf = (C.c_double * n).from_address(p.value)
     arr = np.frombuffer(buf, dtype=np.float64).reshape(shape)
-    arr._wafer_pinned = p  # keep the address alive with the array; freed by pinned_free
+    _PINNED[arr.ctypes.data] = p
     return arr
 
 
+_PINNED = {}
+
+
 def pinned_free(arr):
-    _capi.load().wafer_host_free(arr._wafer_pinned)
+    """Release a pinned_empty() array; the array (and every view of it) must not be used afterwards."""
+    _capi.load().wafer_host_free(_PINNED.pop(arr.ctypes.data))
 
 
 def _p(a):

@@ -41,6 +41,7 @@ struct wafer_ctx {
     int potsub_mode = 0;
     double potsub_scalar = 0.0;
     std::vector<double*> lowers;
+    double* staging = nullptr;  // host-layout bounce buffer for set/get (lazily allocated, never a field buffer)
     double* partials = nullptr;
     long long partials_cap = 0;
     double* scal = nullptr;
@@ -247,13 +248,18 @@ void owned_range(const wafer_ctx* ctx, long long* hp0, long long* hp1) {
 }
 
 // host_is_chunk: `host` already points at plane hp0 (the _slab entry points) instead of at the global array
+int ensure_staging(wafer_ctx* ctx) {
+    if (!ctx->staging) CK(cudaMalloc(&ctx->staging, ctx->bytes()));
+    return WAFER_OK;
+}
+
 int upload(wafer_ctx* ctx, const double* host, double* dst, bool worksized, bool check_ring, bool host_is_chunk = false) {
     const Geom& g = ctx->g;
     long long hp0, hp1;
     chunk_range(ctx, worksized, &hp0, &hp1);
     const long long py = worksized ? g.ny : g.ny + 2 * g.e, pz = worksized ? g.nz : g.nz + 2 * g.e;
-    double* staging = ctx->psi[ctx->cur ^ 1];
-    if (dst == staging) { ctx->err = "internal: upload into the staging buffer"; return WAFER_ERR_INVALID; }
+    TRY(ensure_staging(ctx));
+    double* staging = ctx->staging;
     CK(cudaMemcpyAsync(staging, host + (host_is_chunk ? 0 : hp0 * py * pz), (size_t)((hp1 - hp0) * py * pz) * sizeof(double),
                        cudaMemcpyHostToDevice, ctx->s_main));
     if (check_ring) CK(cudaMemsetAsync(ctx->ring_flag, 0, sizeof(int), ctx->s_main));
@@ -280,8 +286,8 @@ int download(wafer_ctx* ctx, const double* src, double* host, bool host_is_chunk
     long long hp0, hp1;
     owned_range(ctx, &hp0, &hp1);
     const long long py = g.ny + 2 * g.e, pz = g.nz + 2 * g.e;
-    double* staging = ctx->psi[ctx->cur ^ 1];
-    if (src == staging) { ctx->err = "internal: download from the staging buffer"; return WAFER_ERR_INVALID; }
+    TRY(ensure_staging(ctx));
+    double* staging = ctx->staging;
     pack_kernel<<<ctx->sm_count * 16, 256, 0, ctx->s_main>>>(src, staging, g, hp0, hp1, 0);
     TRY(post_launch(ctx));
     CK(cudaMemcpyAsync(host + (host_is_chunk ? 0 : hp0 * py * pz), staging, (size_t)((hp1 - hp0) * py * pz) * sizeof(double),
@@ -342,9 +348,10 @@ int create_impl(const wafer_params* params, wafer_ctx* ctx) {
 
     // slab decomposition along x
     Geom& g = ctx->g;
-    const long long base = p.nx / ctx->world, rem = p.nx % ctx->world;
-    g.L = (int)(base + (ctx->rank < rem ? 1 : 0));
-    g.x0 = ctx->rank * base + std::min<long long>(ctx->rank, rem);
+    uint64_t sx0, sx1;
+    wafer_slab_partition(p.nx, (uint32_t)ctx->world, (uint32_t)ctx->rank, &sx0, &sx1);
+    g.L = (int)(sx1 - sx0);
+    g.x0 = (long long)sx0;
     g.ny = (int)p.ny; g.nz = (int)p.nz; g.e = (int)p.ext; g.gx = g.e;
     g.yp = g.ny + 2 * g.e;
     g.zp = (int)(((long long)g.nz + 2 * g.e + 15) / 16 * 16);
@@ -413,7 +420,7 @@ int wafer_destroy(wafer_ctx* ctx) {
     if (ctx->comm) nccl_api().CommDestroy(ctx->comm);
     for (double* q : ctx->lowers) cudaFree(q);
     cudaFree(ctx->psi[0]); cudaFree(ctx->psi[1]); cudaFree(ctx->v); cudaFree(ctx->a); cudaFree(ctx->b);
-    cudaFree(ctx->potsub_arr); cudaFree(ctx->partials); cudaFree(ctx->scal); cudaFree(ctx->ring_flag);
+    cudaFree(ctx->staging); cudaFree(ctx->potsub_arr); cudaFree(ctx->partials); cudaFree(ctx->scal); cudaFree(ctx->ring_flag);
     if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
     if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
     if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
@@ -433,6 +440,15 @@ int wafer_nccl_unique_id(uint8_t out[128]) {
     NcclUniqueId id;
     if (nccl_api().GetUniqueId(&id) != kNcclSuccess) { g_create_error = "ncclGetUniqueId failed"; return WAFER_ERR_NCCL; }
     memcpy(out, id.internal, 128);
+    return WAFER_OK;
+}
+
+int wafer_slab_partition(uint64_t nx, uint32_t world, uint32_t rank, uint64_t* x0, uint64_t* x1) {
+    if (world == 0) world = 1;
+    if (rank >= world || !x0 || !x1) return WAFER_ERR_INVALID;
+    const uint64_t base = nx / world, rem = nx % world;
+    *x0 = rank * base + std::min<uint64_t>(rank, rem);
+    *x1 = *x0 + base + (rank < rem ? 1 : 0);
     return WAFER_OK;
 }
 
