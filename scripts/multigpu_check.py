@@ -1,0 +1,82 @@
+"""Multi-rank parity check (run under torchrun, one rank per GPU): the x-slab decomposed run must equal the
+single-GPU run of the same lattice — bit-for-bit after ground-state sweeps, to rounding for excited-state steps
+and observables.  Rank 0 prints one JSON line; exit code 1 on mismatch."""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+
+    import wafer_b200
+
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt = torch.tensor(list(wafer_b200.nccl_unique_id()), dtype=torch.uint8, device="cuda")
+    dist.broadcast(idt, 0)
+    nccl_id = bytes(idt.cpu().tolist())
+
+    results = {}
+    ok = True
+    for ext, cd, shape in ((1, "ThreePoint", (96, 40, 72)), (2, "FivePoint", (50, 33, 40)), (3, "SevenPoint", (41, 24, 30))):
+        dn, dt, mass = 0.1, 2e-3, 1.0
+        rng = np.random.default_rng(11)
+        P = tuple(s + 2 * ext for s in shape)
+        v = rng.normal(size=P)
+        phi = np.zeros(P)
+        phi[ext:-ext, ext:-ext, ext:-ext] = rng.normal(size=shape)
+        q = np.zeros(P)
+        q[ext:-ext, ext:-ext, ext:-ext] = rng.normal(size=shape)
+        q /= np.sqrt((q * q).sum())
+        kw = dict(dn=dn, dt=dt, mass=mass, device=local)
+        single = wafer_b200.Lattice(shape, cd, **kw)
+        multi = wafer_b200.Lattice(shape, cd, rank=rank, world=world, nccl_id=nccl_id, **kw)
+        outs = []
+        for lat in (single, multi):
+            lat.set_potential(v)
+            lat.set_phi(phi)
+            lat.evolve(0, 7)
+            o1 = lat.check(0)
+            g = lat.get_phi()
+            lat.push_lower(q)
+            lat.evolve(1, 3)
+            o2 = lat.check(1)
+            e = lat.get_phi()
+            outs.append((o1, g, o2, e))
+        (s1, sg, s2, se), (m1, mg, m2, me) = outs
+        x0, x1 = multi.slab
+        own = slice(x0 + ext, x1 + ext)
+        bit = bool(np.array_equal(sg[own], mg[own]))
+        l2 = float(np.linalg.norm(se[own] - me[own]) / max(np.linalg.norm(se[own]), 1e-300))
+        de = max(abs(s1[k] - m1[k]) / max(abs(s1[k]), 1e-300) for k in s1)
+        de2 = max(abs(s2[k] - m2[k]) / max(abs(s2[k]), 1e-300) for k in s2)
+        flags = torch.tensor([float(bit), l2, de, de2], dtype=torch.float64, device="cuda")
+        allf = [torch.zeros_like(flags) for _ in range(world)]
+        dist.all_gather(allf, flags)
+        allf = torch.stack(allf).cpu().numpy()
+        res = dict(ground_bitwise=bool(allf[:, 0].all()), excited_l2=float(allf[:, 1].max()),
+                   obs_rel=float(allf[:, 2].max()), obs_rel_excited=float(allf[:, 3].max()))
+        results[cd] = res
+        ok = ok and res["ground_bitwise"] and res["excited_l2"] < 1e-12 and res["obs_rel"] < 1e-12 and res["obs_rel_excited"] < 1e-11
+        single.close()
+        multi.close()
+    if rank == 0:
+        print(json.dumps({"world": world, "ok": ok, "results": results}), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -422,3 +422,23 @@ def test_sweep_linearity_512_cubed(wb):
             lat.evolve(0, 3)
             outs.append(lat.get_phi())
     assert np.abs(outs[2] - (2.0 * outs[0] - 0.5 * outs[1])).max() < 1e-13
+
+
+# ---------------------------------------------------------------------------------------------- N > 1 (needs >= 2 GPUs on the box)
+def test_multi_gpu_slab_parity():
+    """x-slab decomposition over NCCL: torchrun scripts/multigpu_check.py on every GPU of the box (2..8)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(min(n, 8)),
+           "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(root, "scripts", "multigpu_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+    assert json.loads(line)["ok"]
