@@ -132,6 +132,9 @@ int wafer_host_alloc(void **ptr, size_t bytes);        /* pinned host memory for
 int wafer_host_free(void *ptr);
 int wafer_device_info(const wafer_ctx *ctx, char *name, size_t name_len, int32_t *sm_count, int32_t *cc_major,
                       int32_t *cc_minor, uint64_t *mem_bytes);
+/* self-test of the sweep's division by the loop-invariant denominator: compares it bit-for-bit with IEEE
+   division on n pseudo-random operands (every exponent, zeros, denormals, NaN/Inf); *mismatches must be 0 */
+int wafer_selftest_division(wafer_ctx *ctx, double den, uint64_t n, uint64_t seed, uint64_t *mismatches);
 const char *wafer_version(void);
 const char *wafer_sweep_variant(const wafer_ctx *ctx); /* name of the sweep kernel variant in use */
 

@@ -21,11 +21,14 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
-    if rank == 0:
-        idt = torch.tensor(list(wafer_b200.nccl_unique_id()), dtype=torch.uint8, device="cuda")
-    dist.broadcast(idt, 0)
-    nccl_id = bytes(idt.cpu().tolist())
+
+    def fresh_nccl_id():
+        """a ncclUniqueId is good for exactly one communicator: make and broadcast a new one per Lattice"""
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt = torch.tensor(list(wafer_b200.nccl_unique_id()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(idt, 0)
+        return bytes(idt.cpu().tolist())
 
     results = {}
     ok = True
@@ -41,7 +44,7 @@ def main():
         q /= np.sqrt((q * q).sum())
         kw = dict(dn=dn, dt=dt, mass=mass, device=local)
         single = wafer_b200.Lattice(shape, cd, **kw)
-        multi = wafer_b200.Lattice(shape, cd, rank=rank, world=world, nccl_id=nccl_id, **kw)
+        multi = wafer_b200.Lattice(shape, cd, rank=rank, world=world, nccl_id=fresh_nccl_id(), **kw)
         outs = []
         for lat in (single, multi):
             lat.set_potential(v)

@@ -124,6 +124,45 @@ def test_sweep_bitwise(wb, oracle, ext, shape, flags):
     assert np.array_equal(got, phi)
 
 
+def test_division_by_invariant(wb):
+    """The time-tiled sweep divides by the loop-invariant `den` with a hoisted reciprocal + the compiler's own
+    residual correction; it must equal IEEE division bit for bit on every operand."""
+    with wb.Lattice((4, 4, 4)) as lat:
+        for den in (2 * 0.01 * 0.01 * 15.9994, 2 * 0.05 * 0.05 * 1.0, 24 * 0.1 * 0.1 * 0.7, 360 * 0.3 * 0.3 * 1.3, 3.0,
+                    1.0, 0.1, 7.0 / 3.0, 1e-20, 1e20, 1e-40, 1.9999999999999998, 1.0000000000000002):
+            for seed in (0, 12345):
+                assert lat.selftest_division(den, 1 << 24, seed) == 0, den
+
+
+@pytest.mark.parametrize("steps", [1, 2, 3, 4, 7, 10])
+@pytest.mark.parametrize("shape", [(12, 9, 10), (50, 37, 21), (33, 64, 130), (70, 61, 121), (7, 3, 2), (131, 31, 59)])
+def test_time_tiled_sweep_bitwise(wb, oracle, shape, steps):
+    """ThreePoint ground state uses the two-steps-per-pass TMA kernel (+ one plain sweep when steps is odd)."""
+    g, v, phi = _rand_state(oracle, shape, 1, 29)
+    a, b = oracle.build_ab(v, g.dt)
+    with wb.Lattice(shape, dn=g.dn, dt=g.dt, mass=g.mass) as lat:
+        assert lat.sweep_variant.startswith("tb2")
+        lat.set_potential(v)
+        lat.set_phi(phi)
+        lat.evolve(0, steps)
+        got = lat.get_phi()
+    oracle.evolve(g, phi, a, b, steps)
+    assert np.array_equal(got, phi)
+
+
+def test_simple_sweep_flag_bitwise(wb, oracle):
+    g, v, phi = _rand_state(oracle, (40, 33, 70), 1, 31)
+    a, b = oracle.build_ab(v, g.dt)
+    with wb.Lattice((40, 33, 70), dn=g.dn, dt=g.dt, mass=g.mass, flags=4) as lat:
+        assert lat.sweep_variant.startswith("simple")
+        lat.set_potential(v)
+        lat.set_phi(phi)
+        lat.evolve(0, 6)
+        got = lat.get_phi()
+    oracle.evolve(g, phi, a, b, 6)
+    assert np.array_equal(got, phi)
+
+
 def test_evolve_zero_steps_still_sweeps_once(wb, oracle):
     """grid.rs:562-686 is a do-while"""
     g, v, phi = _rand_state(oracle, (8, 8, 8), 1, 3)

@@ -151,6 +151,11 @@ class Lattice:
     def sweep_variant(self):
         return self._lib.wafer_sweep_variant(self._h).decode()
 
+    def selftest_division(self, den, n=1 << 24, seed=0):
+        bad = C.c_uint64()
+        self._ck(self._lib.wafer_selftest_division(self._h, den, n, seed, C.byref(bad)))
+        return bad.value
+
     def device_info(self):
         name = C.create_string_buffer(256)
         sm, ma, mi, mem = C.c_int32(), C.c_int32(), C.c_int32(), C.c_uint64()

@@ -17,6 +17,7 @@
 #include "generators.cuh"
 #include "kernels.cuh"
 #include "nccl_dyn.h"
+#include "sweep_tb.cuh"
 
 using namespace wafer;
 
@@ -33,6 +34,10 @@ struct wafer_ctx {
     int dev = 0, sm_count = 0;
     int rank = 0, world = 1;
     bool onfly = true;
+    bool use_tb = false;            // time-tiled TMA sweep available (ThreePoint, V on the fly)
+    CUtensorMap tm_psi[2], tm_v;    // TMA descriptors of the interior of psi[0], psi[1], v
+    int tb_xchunk = 64;
+    int den_ok = 0;
     cudaStream_t s_main = nullptr, s_halo = nullptr;
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_main = nullptr, ev_halo = nullptr;
     double* psi[2] = {nullptr, nullptr};
@@ -153,19 +158,77 @@ int launch_sweep(wafer_ctx* ctx, const double* cur, double* nxt, int xb, int xe,
     }
 }
 
+// ---- time-tiled TMA sweep (sweep_tb.cuh): two steps per launch ----------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_tensor_map(wafer_ctx* ctx, CUtensorMap* tm, double* field, int box_rows) {
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) { ctx->err = "cuTensorMapEncodeTiled not available"; return WAFER_ERR_CUDA; }
+        encode = (EncodeTiledFn)fn;
+    }
+    const Geom& g = ctx->g;
+    // the tensor is the lattice interior only: (nz, ny, L+2gx) with the device pitches; everything outside it
+    // (y ghost rows, z pads, planes beyond the ghosts) is produced by the TMA zero fill
+    cuuint64_t dims[3] = {(cuuint64_t)g.nz, (cuuint64_t)g.ny, (cuuint64_t)(g.L + 2 * g.gx)};
+    cuuint64_t strides[2] = {(cuuint64_t)g.zp * sizeof(double), (cuuint64_t)g.plane * sizeof(double)};
+    cuuint32_t box[3] = {(cuuint32_t)tb::BW, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, field + (long long)g.e * g.zp, dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { ctx->err = "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")"; return WAFER_ERR_CUDA; }
+    return WAFER_OK;
+}
+
+int init_tb(wafer_ctx* ctx) {
+    ctx->use_tb = false;
+    if (ctx->p.ext != 1 || !ctx->onfly || (ctx->p.flags & WAFER_FLAG_SIMPLE_SWEEP)) return WAFER_OK;
+    TRY(make_tensor_map(ctx, &ctx->tm_psi[0], ctx->psi[0], tb::R0));
+    TRY(make_tensor_map(ctx, &ctx->tm_psi[1], ctx->psi[1], tb::R0));
+    TRY(make_tensor_map(ctx, &ctx->tm_v, ctx->v, tb::R1));
+    CK(cudaFuncSetAttribute(tb::sweep_tb2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb::SMEM_BYTES));
+    const double den = denominator(ctx);
+    ctx->den_ok = (den > 7.888609052210118e-31 && den < 1.2676506002282294e30) ? 1 : 0;  // 2^-100 .. 2^100
+    // x chunk: enough CTAs for ~8 waves, at most 128 planes (pipeline fill is 4 planes per chunk)
+    const long long tiles = (long long)ceil_div(ctx->g.nz, tb::TZ) * ceil_div(ctx->g.ny, tb::TY);
+    int chunk = 128;
+    while (chunk > 16 && tiles * ceil_div(ctx->g.L, chunk) < (long long)ctx->sm_count * 6) chunk /= 2;
+    ctx->tb_xchunk = chunk;
+    ctx->use_tb = true;
+    return WAFER_OK;
+}
+
+// two lattice steps: psi[src] -> psi[src^1] for planes [xb, xe)
+int launch_sweep_tb2(wafer_ctx* ctx, int src, int xb, int xe, cudaStream_t st) {
+    if (xe <= xb) return WAFER_OK;
+    const Geom& g = ctx->g;
+    const int chunk = std::min(ctx->tb_xchunk, std::max(xe - xb, 1));
+    dim3 grid(ceil_div(g.nz, tb::TZ), ceil_div(g.ny, tb::TY), ceil_div(xe - xb, chunk));
+    tb::sweep_tb2_kernel<<<grid, tb::THREADS, tb::SMEM_BYTES, st>>>(ctx->tm_psi[src], ctx->tm_v, ctx->psi[src ^ 1], g, xb, xe,
+                                                                    chunk, ctx->p.dt, denominator(ctx), ctx->den_ok);
+    return post_launch(ctx);
+}
+
 // ghost-plane halo exchange of `buf` with the x neighbours (NCCL send/recv over NVLink)
 int exchange(wafer_ctx* ctx, double* buf, cudaStream_t st) {
     if (ctx->world <= 1) return WAFER_OK;
     const Geom& g = ctx->g;
-    const size_t cnt = (size_t)g.e * g.plane;
+    // gx planes each way (gx = 2 for the time-tiled ThreePoint sweep, else ext): whole planes are contiguous
+    const size_t cnt = (size_t)g.gx * g.plane;
     NcclApi& n = nccl_api();
     NK(n.GroupStart());
     if (ctx->rank > 0) {
         NK(n.Send(buf + g.off(0, -g.e, 0), cnt, kNcclFloat64, ctx->rank - 1, ctx->comm, st));
-        NK(n.Recv(buf + g.off(-g.e, -g.e, 0), cnt, kNcclFloat64, ctx->rank - 1, ctx->comm, st));
+        NK(n.Recv(buf + g.off(-g.gx, -g.e, 0), cnt, kNcclFloat64, ctx->rank - 1, ctx->comm, st));
     }
     if (ctx->rank < ctx->world - 1) {
-        NK(n.Send(buf + g.off(g.L - g.e, -g.e, 0), cnt, kNcclFloat64, ctx->rank + 1, ctx->comm, st));
+        NK(n.Send(buf + g.off(g.L - g.gx, -g.e, 0), cnt, kNcclFloat64, ctx->rank + 1, ctx->comm, st));
         NK(n.Recv(buf + g.off(g.L, -g.e, 0), cnt, kNcclFloat64, ctx->rank + 1, ctx->comm, st));
     }
     NK(n.GroupEnd());
@@ -352,7 +415,8 @@ int create_impl(const wafer_params* params, wafer_ctx* ctx) {
     wafer_slab_partition(p.nx, (uint32_t)ctx->world, (uint32_t)ctx->rank, &sx0, &sx1);
     g.L = (int)(sx1 - sx0);
     g.x0 = (long long)sx0;
-    g.ny = (int)p.ny; g.nz = (int)p.nz; g.e = (int)p.ext; g.gx = g.e;
+    g.ny = (int)p.ny; g.nz = (int)p.nz; g.e = (int)p.ext;
+    g.gx = g.e == 1 ? 2 : g.e;  // the time-tiled ThreePoint sweep advances two steps per halo exchange
     g.yp = g.ny + 2 * g.e;
     g.zp = (int)(((long long)g.nz + 2 * g.e + 15) / 16 * 16);
     g.plane = (long long)g.yp * g.zp;
@@ -380,6 +444,7 @@ int create_impl(const wafer_params* params, wafer_ctx* ctx) {
     CK(cudaMemsetAsync(ctx->scal, 0, SL_COUNT * sizeof(double), ctx->s_main));
     CK(cudaMallocHost(&ctx->h_scal, SL_COUNT * sizeof(double)));
     CK(cudaMalloc(&ctx->ring_flag, sizeof(int)));
+    TRY(init_tb(ctx));
 
     if (ctx->world > 1) {
         if (!p.nccl_id) { ctx->err = "world > 1 needs the 128-byte nccl_id of rank 0"; return WAFER_ERR_INVALID; }
@@ -676,27 +741,40 @@ int wafer_evolve(wafer_ctx* ctx, uint8_t wnum_in, uint64_t steps) {
     const Geom& g = ctx->g;
     const int wnum = std::min<int>(wnum_in, (int)ctx->lowers.size());
     const bool excited = wnum_in > 0;  // grid.rs:674: norm/normalise run for wnum > 0 even with an empty w_store
-    const bool overlap = ctx->world > 1 && !excited && g.L > 2 * g.e;
+    const bool overlap = ctx->world > 1 && !excited && g.L > 2 * g.gx;
     if (overlap) {
         CK(cudaEventRecord(ctx->ev_main, ctx->s_main));
         CK(cudaEventRecord(ctx->ev_halo, ctx->s_main));
     }
+    const uint64_t total = steps == 0 ? 1 : steps;  // grid.rs:562-686 is a do-while: steps == 0 still sweeps once
     uint64_t done = 0;
-    do {  // grid.rs:562-686 is a do-while: steps == 0 still performs one sweep
-        const double* cur = ctx->psi[ctx->cur];
-        double* nxt = ctx->psi[ctx->cur ^ 1];
+    while (done < total) {
+        // ground state: two steps per HBM pass with the time-tiled TMA kernel whenever two steps remain;
+        // excited states need a global norm / Gram-Schmidt after EVERY step (grid.rs:674-681): one step per pass
+        const bool two = ctx->use_tb && !excited && total - done >= 2;
+        const int b = two ? 2 : g.e;  // boundary planes whose new values the neighbours need
+        const int src = ctx->cur;
+        const double* cur = ctx->psi[src];
+        double* nxt = ctx->psi[src ^ 1];
         if (overlap) {
             // boundary planes + NVLink halo exchange on the high-priority stream, interior on the main stream
             CK(cudaStreamWaitEvent(ctx->s_halo, ctx->ev_main, 0));
             CK(cudaStreamWaitEvent(ctx->s_main, ctx->ev_halo, 0));
-            TRY(launch_sweep(ctx, cur, nxt, 0, g.e, false, 0, ctx->s_halo));
-            TRY(launch_sweep(ctx, cur, nxt, g.L - g.e, g.L, false, 0, ctx->s_halo));
+            if (two) {
+                TRY(launch_sweep_tb2(ctx, src, 0, b, ctx->s_halo));
+                TRY(launch_sweep_tb2(ctx, src, g.L - b, g.L, ctx->s_halo));
+            } else {
+                TRY(launch_sweep(ctx, cur, nxt, 0, b, false, 0, ctx->s_halo));
+                TRY(launch_sweep(ctx, cur, nxt, g.L - b, g.L, false, 0, ctx->s_halo));
+            }
             TRY(exchange(ctx, nxt, ctx->s_halo));
             CK(cudaEventRecord(ctx->ev_halo, ctx->s_halo));
-            TRY(launch_sweep(ctx, cur, nxt, g.e, g.L - g.e, false, 0, ctx->s_main));
+            if (two) TRY(launch_sweep_tb2(ctx, src, b, g.L - b, ctx->s_main));
+            else TRY(launch_sweep(ctx, cur, nxt, b, g.L - b, false, 0, ctx->s_main));
             CK(cudaEventRecord(ctx->ev_main, ctx->s_main));
         } else {
-            TRY(launch_sweep(ctx, cur, nxt, 0, g.L, excited, 0, ctx->s_main));
+            if (two) TRY(launch_sweep_tb2(ctx, src, 0, g.L, ctx->s_main));
+            else TRY(launch_sweep(ctx, cur, nxt, 0, g.L, excited, 0, ctx->s_main));
             TRY(exchange(ctx, nxt, ctx->s_main));
         }
         ctx->cur ^= 1;
@@ -704,8 +782,8 @@ int wafer_evolve(wafer_ctx* ctx, uint8_t wnum_in, uint64_t steps) {
             TRY(finalize(ctx, 1, sweep_blocks(ctx, 0, g.L), SL_NORM, ctx->s_main));
             TRY(gs_chain(ctx, SL_NORM, wnum));
         }
-        done += 1;
-    } while (done < steps);
+        done += two ? 2 : 1;
+    }
     if (overlap) CK(cudaStreamWaitEvent(ctx->s_main, ctx->ev_halo, 0));
     return WAFER_OK;
 }
@@ -813,8 +891,27 @@ int wafer_device_info(const wafer_ctx* ctx, char* name, size_t name_len, int32_t
     return WAFER_OK;
 }
 
+int wafer_selftest_division(wafer_ctx* ctx, double den, uint64_t n, uint64_t seed, uint64_t* mismatches) {
+    if (!ctx) return WAFER_ERR_INVALID;
+    REQUIRE(mismatches, "mismatches is NULL");
+    CK(cudaSetDevice(ctx->dev));
+    unsigned long long* d = nullptr;
+    CK(cudaMalloc(&d, sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(d, 0, sizeof(unsigned long long), ctx->s_main));
+    const int ok = (den > 7.888609052210118e-31 && den < 1.2676506002282294e30) ? 1 : 0;
+    tb::div_selftest_kernel<<<ctx->sm_count * 8, 256, 0, ctx->s_main>>>(den, ok, n, seed, d);
+    TRY(post_launch(ctx));
+    unsigned long long h = 0;
+    CK(cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->s_main));
+    CK(cudaStreamSynchronize(ctx->s_main));
+    cudaFree(d);
+    *mismatches = h;
+    return WAFER_OK;
+}
+
 const char* wafer_sweep_variant(const wafer_ctx* ctx) {
     if (!ctx) return "";
+    if (ctx->use_tb) return "tb2-tma/V-onfly";
     return ctx->onfly ? "simple-regqueue/V-onfly" : "simple-regqueue/AB-arrays";
 }
 
