@@ -2,13 +2,14 @@
 # the CPU oracle under oracle/.  `python -c "import __graft_entry__ as g; g.build()"` runs `make all`.
 NVCC      ?= /usr/local/cuda/bin/nvcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
-NVCCFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -fmad=false -Xcompiler -fPIC,-Wall,-Wno-unused-function --expt-relaxed-constexpr
+TBFLAGS   ?=
+NVCCFLAGS := $(ARCH) $(TBFLAGS) -O3 -std=c++17 -lineinfo -fmad=false -Xcompiler -fPIC,-Wall,-Wno-unused-function --expt-relaxed-constexpr
 CSRC      := wafer_b200/csrc
 LIB       := wafer_b200/libwafer_b200.so
 
 all: $(LIB) oracle
 
-$(LIB): $(CSRC)/wafer_b200.cu $(CSRC)/kernels.cuh $(CSRC)/generators.cuh $(CSRC)/nccl_dyn.h include/wafer_b200.h Makefile
+$(LIB): $(wildcard $(CSRC)/*.cu $(CSRC)/*.cuh $(CSRC)/*.h) include/wafer_b200.h Makefile
 	$(NVCC) $(NVCCFLAGS) -Xptxas -v -shared -o $@ $(CSRC)/wafer_b200.cu -ldl 2> $(CSRC)/ptxas.log || (cat $(CSRC)/ptxas.log; exit 1)
 	@grep -E "error|warning" $(CSRC)/ptxas.log | grep -v "ptxas info" || true
 

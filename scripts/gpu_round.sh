@@ -13,12 +13,16 @@ for s in $STAGES; do
     smoke)  timeout 300 python __graft_entry__.py smoke > "$OUT/smoke.log" 2>&1; echo "smoke rc=$?" | tee -a "$OUT/rc.log"; tail -3 "$OUT/smoke.log";;
     bench)  timeout 900 python bench.py --steps 3 --warmup 3 > "$OUT/bench.json" 2> "$OUT/bench.err"; echo "bench rc=$?" | tee -a "$OUT/rc.log"; cat "$OUT/bench.json"; tail -3 "$OUT/bench.err";;
     benchab) timeout 600 python bench.py --steps 3 --warmup 3 --flags 1 --no-e2e --no-cpu > "$OUT/bench_ab.json" 2> "$OUT/bench_ab.err"; echo "benchab rc=$?" | tee -a "$OUT/rc.log"; cat "$OUT/bench_ab.json";;
+    quick)  timeout 600 python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu > "$OUT/bench_quick.json" 2> "$OUT/bench_quick.err"; echo "quick rc=$?" | tee -a "$OUT/rc.log"; python -c "
+import json,sys
+d=json.loads(open('$OUT/bench_quick.json').read().strip().splitlines()[-1]); print('QUICK value=%.1f GLUPS frac=%.3f variant=%s 512^3=%.1f clocks=%s' % (d['value'], d['roofline']['frac'], d['sweep_variant'], d['extra'].get('glups_512cubed_1gpu',0), d['clocks']))"; tail -2 "$OUT/bench_quick.err";;
+    tbtest) timeout 900 python -m pytest tests -m gpu -x -q -k "time_tiled or division or sweep_bitwise or default_wafer or simple_sweep" > "$OUT/pytest_tb.log" 2>&1; echo "tbtest rc=$?" | tee -a "$OUT/rc.log"; tail -3 "$OUT/pytest_tb.log";;
     ref)    timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > "$OUT/bench_ref.json" 2> "$OUT/bench_ref.err"; echo "ref rc=$?" | tee -a "$OUT/rc.log"; cat "$OUT/bench_ref.json";;
     ncu)
       timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/launches.csv" \
         python bench.py --grid 512 --sweeps 20 --steps 2 --warmup 1 --no-e2e --no-cpu --no-512 > "$OUT/ncu_launch_bench.log" 2>&1
       echo "ncu-launches rc=$?" | tee -a "$OUT/rc.log"
-      timeout 900 ncu --set full --clock-control none --import-source on -k regex:sweep -s 30 -c 2 -f -o "$OUT/sweep_full" \
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:sweep -s 6 -c 2 -f -o "$OUT/sweep_full" \
         python bench.py --grid 512 --sweeps 20 --steps 2 --warmup 1 --no-e2e --no-cpu --no-512 > "$OUT/ncu_full_bench.log" 2>&1
       echo "ncu-full rc=$?" | tee -a "$OUT/rc.log";;
   esac
