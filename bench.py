@@ -186,16 +186,17 @@ def hbm_peak():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(n, variant):
-    """dram bytes per sweep launch from the committed ncu --set full capture, if one matches this workload."""
+def ncu_traffic(variant, updates_per_launch):
+    """dram__bytes_read+write per launch of the sweep kernel, from the committed `ncu --set full` capture of the
+    same kernel (profiles/ncu_traffic.json: measured at 512^3, scaled by updates per launch)."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             for rec in json.load(f):
-                if rec["grid"] == n and rec["variant"] == variant:
-                    return rec["dram_bytes_per_launch"]
+                if rec["variant"] == variant:
+                    return rec["dram_bytes_per_update"] * updates_per_launch, rec["note"]
     except Exception:
         pass
-    return None
+    return None, None
 
 
 def b200_main(args):
@@ -235,14 +236,21 @@ def b200_main(args):
     sweeps_total = args.sweeps * args.steps
 
     peak, peak_src = hbm_peak()
-    # dominant kernel = the sweep: one launch per lattice sweep per rank (boundary launches in multi-GPU are tiny)
-    launch_ms = ms / sweeps_total
-    updates_per_launch = n ** 3 / world
+    # dominant kernel = the sweep.  The time-tiled kernel advances TWO lattice steps per launch, the plain one a
+    # single step; multi-GPU runs add two small boundary-plane launches per pass on the halo stream.  The figure is
+    # per main-stream launch: the timed region holds nothing but back-to-back sweep launches.
+    steps_per_launch = 2 if lat.sweep_variant.startswith("tb2") else 1
+    n_main = sweeps_total // steps_per_launch + sweeps_total % steps_per_launch
+    launch_ms = ms / n_main
+    updates_per_launch = n ** 3 / world * sweeps_total / n_main
     achieved = BYTES_PER_UPDATE * updates_per_launch / (launch_ms * 1e-3) / 1e9
+    traffic, traffic_note = ncu_traffic(lat.sweep_variant, updates_per_launch)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(n, lat.sweep_variant), "peak_source": peak_src, "kernel": lat.sweep_variant,
+                "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src, "kernel": lat.sweep_variant,
                 "algorithmic_bytes_per_update": BYTES_PER_UPDATE, "updates_per_launch": updates_per_launch,
-                "launch_ms": launch_ms, "frac_of_nominal_8TBps": achieved / 8000.0}
+                "steps_per_launch": steps_per_launch, "launch_ms": launch_ms,
+                "dram_frac_of_peak": (traffic / (launch_ms * 1e-3) / 1e9 / peak) if traffic else None,
+                "frac_of_nominal_8TBps": achieved / 8000.0}
 
     # ---- e2e: host buffers in and out of every step (pinned), through the C ABI
     e2e = None
