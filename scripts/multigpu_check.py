@@ -50,8 +50,8 @@ def main():
             lat.set_potential(v)
             lat.set_phi(phi)
             lat.evolve(0, 7)
-            o1 = lat.check(0)
-            g = lat.get_phi()
+            g = lat.get_phi()    # before the check: its normalise divides by a sum whose last bit depends on the
+            o1 = lat.check(0)    # reduction order (per-rank partials + all-reduce), the sweep itself does not
             lat.push_lower(q)
             lat.evolve(1, 3)
             o2 = lat.check(1)
