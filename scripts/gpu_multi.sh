@@ -10,7 +10,7 @@ nvidia-smi topo -m > "$OUT/topo.txt" 2>&1
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29601 \
     scripts/multigpu_check.py > "$OUT/multigpu_check.log" 2>&1
 echo "multigpu_check rc=$?" | tee -a "$OUT/rc.log"; grep '^{' "$OUT/multigpu_check.log" | tail -1; tail -3 "$OUT/multigpu_check.log"
-for n in 1 2 4 8; do
+for n in ${NLIST:-1 2 4 8}; do
   [ $n -gt $N ] && break
   if [ $n -eq 1 ]; then
     timeout 900 python bench.py --gpus 1 --steps 3 --warmup 3 --no-cpu --no-512 $EXTRA > "$OUT/scale_$n.json" 2> "$OUT/scale_$n.err"
