@@ -7,17 +7,23 @@ NVCCFLAGS := $(ARCH) $(TBFLAGS) -O3 -std=c++17 -lineinfo -fmad=false -Xcompiler 
 CSRC      := wafer_b200/csrc
 LIB       := wafer_b200/libwafer_b200.so
 
-all: $(LIB) oracle
+BIN       := wafer_b200/wafer-b200
+
+all: $(LIB) $(BIN) oracle
 
 $(LIB): $(wildcard $(CSRC)/*.cu $(CSRC)/*.cuh $(CSRC)/*.h) include/wafer_b200.h Makefile
 	$(NVCC) $(NVCCFLAGS) -Xptxas -v -shared -o $@ $(CSRC)/wafer_b200.cu -ldl 2> $(CSRC)/ptxas.log || (cat $(CSRC)/ptxas.log; exit 1)
 	@grep -E "error|warning" $(CSRC)/ptxas.log | grep -v "ptxas info" || true
 
+# the reference's driver (main.rs / grid.rs run+solve) over the C ABI; host C++ only
+$(BIN): $(CSRC)/host/wafer_main.cpp $(CSRC)/host/config.hpp include/wafer_b200.h $(LIB)
+	/usr/bin/g++ -O2 -std=c++17 -Wall -Wextra -o $@ $(CSRC)/host/wafer_main.cpp -Lwafer_b200 -lwafer_b200 -Wl,-rpath,'$$ORIGIN' -lpthread
+
 oracle:
 	$(MAKE) -C oracle
 
 clean:
-	rm -f $(LIB) $(CSRC)/ptxas.log
+	rm -f $(LIB) $(BIN) $(CSRC)/ptxas.log
 	$(MAKE) -C oracle clean
 
 .PHONY: all oracle clean

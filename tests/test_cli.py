@@ -1,0 +1,98 @@
+"""The C++ front end `wafer-b200` (reference: src/main.rs, src/config.rs:292-370, src/grid.rs:31-246)."""
+import json
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "wafer_b200", "wafer-b200")
+DEFAULT = os.path.join(ROOT, "tests", "golden", "wafer_default.yaml")
+
+
+@pytest.fixture(scope="module")
+def binary():
+    if not os.path.exists(BIN):
+        import __graft_entry__
+        __graft_entry__.build()
+    return BIN
+
+
+def _check(binary, text, tmp_path):
+    cfg = tmp_path / "wafer.yaml"
+    cfg.write_text(text)
+    return subprocess.run([binary, "-c", str(cfg), "--check-config"], capture_output=True, text=True)
+
+
+def test_default_config_parses(binary):
+    r = subprocess.run([binary, "-c", DEFAULT, "--check-config"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    c = json.loads(r.stdout)
+    assert c["grid"] == {"size": {"x": 50, "y": 50, "z": 50}, "dn": 0.01, "dt": 3e-5}
+    assert c["central_difference"] == "ThreePoint" and c["ext"] == 1 and c["max_steps"] is None
+    assert c["wavenum"] == 0 and c["wavemax"] == 1 and c["potential"] == "Harmonic" and c["mass"] == 15.9994
+    assert c["output"] == {"screen_update": 1000, "snap_update": None, "file_type": "Json", "save_wavefns": True,
+                           "save_potential": False}
+
+
+def test_config_checks_follow_the_reference(binary, tmp_path):
+    """Config::parse (config.rs:362-370): dt <= dn^2/3 and wavenum <= wavemax; serde errors for bad fields."""
+    base = open(DEFAULT).read()
+    r = _check(binary, base.replace("dt: 3e-5", "dt: 3.4e-5"), tmp_path)
+    assert r.returncode == 1 and "LargeDt" in r.stderr
+    r = _check(binary, base.replace("dt: 3e-5", "dt: 3.3e-5"), tmp_path)
+    assert r.returncode == 0
+    r = _check(binary, base.replace("wavenum: 0", "wavenum: 2"), tmp_path)
+    assert r.returncode == 1 and "LargeWavenum" in r.stderr
+    r = _check(binary, base.replace("potential: Harmonic", "potential: Anharmonic"), tmp_path)
+    assert r.returncode == 1 and "unknown variant" in r.stderr
+    r = _check(binary, base.replace("mass: 15.9994\n", ""), tmp_path)
+    assert r.returncode == 1 and "missing field `mass`" in r.stderr
+    r = _check(binary, base.replace("# max_steps: 50000000", "max_steps: 5000").replace("# snap_update: 10000",
+                                                                                         "snap_update: 2000"), tmp_path)
+    c = json.loads(r.stdout)
+    assert c["max_steps"] == 5000 and c["output"]["snap_update"] == 2000
+    r = _check(binary, base.replace("central_difference: ThreePoint", "central_difference: SevenPoint"), tmp_path)
+    assert json.loads(r.stdout)["ext"] == 3
+
+
+@pytest.mark.skipif(os.path.exists("/dev/nvidiactl"), reason="a GPU is present")
+def test_run_without_gpu_fails_loudly(binary, tmp_path):
+    r = subprocess.run([binary, "-c", DEFAULT, "--no-output"], capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 1 and "no CUDA device" in r.stderr
+
+
+@pytest.mark.gpu
+def test_default_run_matches_oracle(binary, oracle, tmp_path):
+    """BASELINE config C1 end to end through the front end: table rows, observables file, saved wavefunctions."""
+    r = subprocess.run([binary, "-c", DEFAULT, "--output-root", str(tmp_path / "out")], capture_output=True, text=True,
+                       cwd=tmp_path, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    rows = [l for l in r.stdout.splitlines() if re.match(r"\s+│\s+[0-9.]+ │", l)]
+    g = oracle.make_grid(50, 50, 50, ext=1, dn=0.01, dt=3e-5, mass=15.9994)
+    v = oracle.potential(g, "Harmonic")
+    a, b = oracle.build_ab(v, g.dt)
+    phi = oracle.initial_condition(g, "Boolean")
+    conv, rec = oracle.solve(g, v, a, b, phi, tolerance=1e-4, screen_update=1000)
+    assert conv and len(rec) == 19
+    ground_rows = rows[:19]
+    for row, ref in zip(ground_rows, rec):
+        cols = [c.strip() for c in row.split("│")[1:5]]
+        assert float(cols[0]) == pytest.approx(ref["tau"], abs=5e-4)
+        assert float(cols[1]) == pytest.approx(ref["E"], rel=1e-9)
+    outdir = next((tmp_path / "out").iterdir())
+    obs = json.loads((outdir / "observables_0.json").read_text())
+    assert obs["state"] == 0 and obs["energy"] == pytest.approx(rec[-1]["E"], rel=1e-9)
+    assert obs["binding_energy"] == pytest.approx(rec[-1]["E"], rel=1e-9)  # Harmonic: pot_sub = 0
+    assert obs["r"] == pytest.approx(np.sqrt(rec[-1]["r2"] / rec[-1]["norm2"]), rel=1e-9)
+    assert obs["l_r"] == pytest.approx(50 / obs["r"], rel=1e-12)
+    wf = np.loadtxt(outdir / "wavefunction_0.csv", delimiter=",")
+    assert wf.shape == (125000, 4)
+    got = wf[:, 3].reshape(50, 50, 50)
+    ref_work = phi[1:-1, 1:-1, 1:-1]
+    assert np.linalg.norm(got - ref_work) / np.linalg.norm(ref_work) < 1e-8
+    assert (outdir / "observables_1.json").exists() and (outdir / "wavefunction_1.csv").exists()
+    e1 = json.loads((outdir / "observables_1.json").read_text())["energy"]
+    assert e1 > obs["energy"]

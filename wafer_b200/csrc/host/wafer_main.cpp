@@ -1,0 +1,405 @@
+// wafer_main.cpp — `wafer-b200`: the reference's driver (src/main.rs:94-240, src/grid.rs:31-246) over the C ABI.
+//
+// Same wafer.yaml, same CLI flags (-c/--config, -s/--script, -d), same per-state loop, same table rows
+// (output.rs:497-521) and observables record (output.rs:32-45, 533-547).  Everything numerical happens in
+// libwafer_b200.so on the GPU; this file is host glue: configuration, potential / initial-condition selection,
+// CSV / JSON files (the plain-text members of the reference's five formats), printing.
+//
+//   wafer-b200 -c wafer.yaml                 run (one process per GPU; RANK / WORLD_SIZE / LOCAL_RANK select a slab)
+//   wafer-b200 -c wafer.yaml --check-config  parse + validate only, print the configuration as JSON (no GPU needed)
+#include <sys/stat.h>
+#include <sys/types.h>
+#include <unistd.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <ctime>
+#include <fstream>
+#include <iostream>
+#include <random>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../../include/wafer_b200.h"
+#include "config.hpp"
+
+using namespace wafer_host;
+
+namespace {
+
+struct Dims {
+    size_t nx, ny, nz, e, px, py, pz;
+    explicit Dims(const Config& c) : nx(c.nx), ny(c.ny), nz(c.nz), e(c.ext()), px(nx + 2 * e), py(ny + 2 * e), pz(nz + 2 * e) {}
+    size_t padded() const { return px * py * pz; }
+    size_t p(size_t i, size_t j, size_t k) const { return (i * py + j) * pz + k; }
+};
+
+std::string ordinal(unsigned n) {
+    const char* suf = "th";
+    if (n % 100 < 11 || n % 100 > 13) {
+        if (n % 10 == 1) suf = "st";
+        else if (n % 10 == 2) suf = "nd";
+        else if (n % 10 == 3) suf = "rd";
+    }
+    return std::to_string(n) + suf;
+}
+
+// ---- plain csv arrays: rows `i,j,k,data` over the WORK area, x-major / z fastest, no header (output.rs:148-166) ----
+void write_csv_work(const std::string& path, const double* padded, const Dims& d) {
+    FILE* f = fopen(path.c_str(), "w");
+    if (!f) throw std::runtime_error("CreateFile: " + path);
+    for (size_t i = 0; i < d.nx; ++i)
+        for (size_t j = 0; j < d.ny; ++j)
+            for (size_t k = 0; k < d.nz; ++k)
+                fprintf(f, "%zu,%zu,%zu,%.17g\n", i, j, k, padded[d.p(i + d.e, j + d.e, k + d.e)]);
+    fclose(f);
+}
+
+// input.rs:607-662 without the trilinear resize: the file must have the configured work size
+bool read_csv_work(const std::string& path, std::vector<double>& padded, const Dims& d) {
+    std::ifstream f(path);
+    if (!f) return false;
+    std::fill(padded.begin(), padded.end(), 0.0);
+    std::string line;
+    size_t n = 0;
+    while (std::getline(f, line)) {
+        if (line.empty()) continue;
+        size_t i, j, k;
+        double v;
+        if (sscanf(line.c_str(), "%zu,%zu,%zu,%lf", &i, &j, &k, &v) != 4) throw std::runtime_error("ParsePlainRecord: " + path);
+        if (i >= d.nx || j >= d.ny || k >= d.nz)
+            throw std::runtime_error("ArrayShape: " + path + " does not match grid.size (resizing is not supported by this build)");
+        padded[d.p(i + d.e, j + d.e, k + d.e)] = v;
+        ++n;
+    }
+    if (n != d.nx * d.ny * d.nz) throw std::runtime_error("ArrayShape: " + path + " does not match grid.size");
+    return true;
+}
+
+// input::script_potential (input.rs:186-248): JSON grid on stdin, one float per stdout line, work area x-major
+void script_potential(const Config& c, std::vector<double>& padded, const Dims& d) {
+    char tmpl[] = "/tmp/wafer_script_XXXXXX";
+    const int fd = mkstemp(tmpl);
+    if (fd < 0) throw std::runtime_error("StdIn: cannot create a temporary file");
+    char buf[256];
+    const int len = snprintf(buf, sizeof buf, "{\"grid\":{\"dn\":%.17g,\"x\":%llu,\"y\":%llu,\"z\":%llu}}", c.dn,
+                             (unsigned long long)c.nx, (unsigned long long)c.ny, (unsigned long long)c.nz);
+    if (write(fd, buf, len) != len) throw std::runtime_error("StdIn: short write");
+    close(fd);
+    const std::string cmd = "\"" + c.script_location + "\" < " + tmpl;
+    FILE* p = popen(cmd.c_str(), "r");
+    if (!p) throw std::runtime_error("SpawnPython: " + c.script_location);
+    std::fill(padded.begin(), padded.end(), 0.0);
+    size_t n = 0;
+    char line[128];
+    while (fgets(line, sizeof line, p)) {
+        char* end = nullptr;
+        const double v = strtod(line, &end);
+        if (end == line) { pclose(p); unlink(tmpl); throw std::runtime_error("ParseFloat: script output"); }
+        if (n < d.nx * d.ny * d.nz) {
+            const size_t i = n / (d.ny * d.nz), j = (n / d.nz) % d.ny, k = n % d.nz;
+            padded[d.p(i + d.e, j + d.e, k + d.e)] = v;
+        }
+        ++n;
+    }
+    const int rc = pclose(p);
+    unlink(tmpl);
+    if (rc != 0) throw std::runtime_error("SpawnPython: script exited with status " + std::to_string(rc));
+    if (n != d.nx * d.ny * d.nz) throw std::runtime_error("ArrayShape: script printed " + std::to_string(n) + " values");
+}
+
+// potential.rs:374-398 (host copies for the FullCornell pot_sub array, potential.rs:326-341 at WORK indices)
+double alphas(double mu) {
+    const double nf = 2.0, b0 = 11. - 2. * nf / 3., b1 = 51. - 19. * nf / 3.;
+    const double b2 = 2857. - 5033. * nf / 9. + 325. * nf * nf / 27., r = 2.3, l = 2. * std::log(mu / r), ll = std::log(l);
+    return 4. * M_PI * (1. - 2. * b1 * ll / (b0 * b0 * l) + 4. * b1 * b1 * ((ll - 0.5) * (ll - 0.5) + b2 * b0 / (8. * b1 * b1) - 5.0 / 4.0) / (b0 * b0 * b0 * b0 * l * l)) / (b0 * l);
+}
+double debye_mu(double t) { return 1.4 * std::sqrt((1. + 2.0 / 6.) * 4. * M_PI * alphas(2. * M_PI * t)) * t * 0.2; }
+
+std::vector<double> full_cornell_pot_sub(const Config& c) {
+    std::vector<double> out(c.nx * c.ny * c.nz);
+    const double xi = 0.0, mu1 = debye_mu(1.0);
+    for (size_t i = 0; i < c.nx; ++i)
+        for (size_t j = 0; j < c.ny; ++j)
+            for (size_t k = 0; k < c.nz; ++k) {
+                const double dx = (double)i - ((double)c.nx + 1.) / 2., dy = (double)j - ((double)c.ny + 1.) / 2.;
+                const double dz = (double)k - ((double)c.nz + 1.) / 2.;
+                const double r = c.dn * std::sqrt(dx * dx + dy * dy + dz * dz);
+                const double md = mu1 * 1. + (0.07 * std::pow(xi, 0.2)) * (1. - c.dn * c.dn * dz * dz / (r * r)) * std::pow(1. + xi, -0.29);
+                out[(i * c.ny + j) * c.nz + k] = c.sig / md + 4. * c.mass;
+            }
+    return out;
+}
+
+struct Run {
+    Config cfg;
+    wafer_ctx* ctx = nullptr;
+    int rank = 0, world = 1;
+    std::string outdir;
+    bool quiet = false;
+    void ck(int rc, const char* what) const {
+        if (rc != WAFER_OK) throw std::runtime_error(std::string(what) + ": " + wafer_last_error(ctx));
+    }
+};
+
+// output.rs:497-521
+std::string measurement_row(double tau, double diff, const wafer_observables& o) {
+    char b[160];
+    if (tau > 0.0)
+        snprintf(b, sizeof b, "     │%11.3f │%19.10e │%15.5f │%15.5e │", tau, o.energy / o.norm2, std::sqrt(o.r2 / o.norm2), diff);
+    else
+        snprintf(b, sizeof b, "     │%11.3f │%19.10e │%15.5f │%15s │", tau, o.energy / o.norm2, std::sqrt(o.r2 / o.norm2), "--   ");
+    return b;
+}
+
+void write_observables(const Run& r, unsigned wnum, const wafer_observables& o) {
+    // ObservablesOutput (output.rs:32-45, 533-547)
+    const double rn = std::sqrt(o.r2 / o.norm2), energy = o.energy / o.norm2, binding = (o.energy - o.v_infinity) / o.norm2;
+    const double l_r = (double)r.cfg.nx / rn;
+    if (!r.quiet) {
+        if (wnum == 0) printf("══▶ Ground state energy = %.15g\n══▶ Ground state binding energy = %.15g\n", energy, binding);
+        else printf("══▶ %s excited state energy = %.15g\n══▶ %s excited state binding energy = %.15g\n", ordinal(wnum).c_str(), energy,
+                    ordinal(wnum).c_str(), binding);
+        printf("══▶ rᵣₘₛ = %.15g\n══▶ L/rᵣₘₛ = %.15g\n\n", rn, l_r);
+    }
+    if (r.outdir.empty() || r.rank != 0) return;
+    const bool csv = r.cfg.file_type == 1;
+    const std::string path = r.outdir + "/observables_" + std::to_string(wnum) + (csv ? ".csv" : ".json");
+    FILE* f = fopen(path.c_str(), "w");
+    if (!f) throw std::runtime_error("CreateFile: " + path);
+    if (csv) fprintf(f, "state,energy,binding_energy,r,l_r\n%u,%.17g,%.17g,%.17g,%.17g\n", wnum, energy, binding, rn, l_r);
+    else fprintf(f, "{\"state\":%u,\"energy\":%.17g,\"binding_energy\":%.17g,\"r\":%.17g,\"l_r\":%.17g}\n", wnum, energy, binding, rn, l_r);
+    fclose(f);
+}
+
+void save_wavefunction(const Run& r, unsigned wnum, bool converged) {
+    if (r.outdir.empty()) return;
+    const Dims d(r.cfg);
+    std::vector<double> phi(d.padded(), 0.0);
+    r.ck(wafer_get_phi(r.ctx, phi.data()), "wafer_get_phi");
+    std::string name = r.outdir + "/wavefunction_" + std::to_string(wnum) + (converged ? "" : "_partial");
+    if (r.world > 1) name += ".rank" + std::to_string(r.rank);  // each rank holds (and writes) only its slab
+    write_csv_work(name + ".csv", phi.data(), d);
+}
+
+// grid.rs:50-246 for one state; returns true when converged
+bool solve(Run& r, unsigned wnum) {
+    const Config& c = r.cfg;
+    const Dims d(c);
+    if (wnum > 0) {
+        // grid.rs:60-96: a wavefunction_{wnum} file in ./input wins, else start from the previous converged state
+        std::vector<double> phi(d.padded());
+        if (read_csv_work("input/wavefunction_" + std::to_string(wnum) + ".csv", phi, d)) {
+            r.ck(wafer_set_phi(r.ctx, phi.data()), "wafer_set_phi");
+        } else {
+            r.ck(wafer_phi_from_lower(r.ctx, wnum - 1), "wafer_phi_from_lower");
+        }
+    }
+    if (!r.quiet && r.rank == 0) {
+        if (wnum == 0) printf("\n═════╤════════════╤════════ Ground state caclulation ════════╤════════════════╤═════\n");
+        else printf("\n═════╤════════════╤═════ %s excited state caclulation ═════╤════════════════╤═════\n", ordinal(wnum).c_str());
+        printf("     │  Time (τ)  │       Energy       │      rᵣₘₛ      │   Difference   │\n");
+        printf("─────┼────────────┼────────────────────┼────────────────┼────────────────┼─────\n");
+    }
+    uint64_t step = 0;
+    double last_energy = 1.7976931348623157e308;
+    bool converged = false;
+    wafer_observables obs{};
+    for (;;) {
+        r.ck(wafer_check(r.ctx, (uint8_t)wnum, &obs), "wafer_check");                                   // grid.rs:127-135
+        if (!std::isfinite(obs.energy) || !std::isfinite(obs.norm2) || obs.norm2 == 0.0)
+            throw std::runtime_error("non-finite observables (the reference's R64 would panic here)");
+        const double norm_energy = obs.energy / obs.norm2, tau = (double)step * c.dt;
+        if (c.snap_update && step % *c.snap_update == 0) {                                               // grid.rs:137-158
+            r.ck(wafer_normalise(r.ctx, obs.norm2), "wafer_normalise");
+            save_wavefunction(r, wnum, false);
+        }
+        const double diff = std::fabs(norm_energy - last_energy);
+        if (!r.quiet && r.rank == 0) { puts(measurement_row(tau, diff, obs).c_str()); fflush(stdout); }
+        if (diff < c.tolerance) { converged = true; break; }                                             // grid.rs:162-192
+        last_energy = norm_energy;
+        if (c.max_steps && step > *c.max_steps) break;                                                   // grid.rs:211-213
+        r.ck(wafer_evolve(r.ctx, (uint8_t)wnum, c.screen_update), "wafer_evolve");                       // grid.rs:216
+        step += c.screen_update;
+    }
+    if (converged) {
+        if (!r.quiet && r.rank == 0) printf("═════╧════════════╧════════════════════╧════════════════╧════════════════╧═════\n");
+        if (r.rank == 0) write_observables(r, wnum, obs);
+        if (c.snap_update && !r.outdir.empty()) {                                                        // grid.rs:174-190
+            std::string partial = r.outdir + "/wavefunction_" + std::to_string(wnum) + "_partial";
+            if (r.world > 1) partial += ".rank" + std::to_string(r.rank);
+            unlink((partial + ".csv").c_str());
+        }
+    }
+    if (c.save_wavefns) save_wavefunction(r, wnum, converged);                                           // grid.rs:223-237
+    if (converged) r.ck(wafer_push_lower_from_phi(r.ctx), "wafer_push_lower_from_phi");                  // grid.rs:241
+    return converged;
+}
+
+// rank 0 writes the ncclUniqueId to a file, the others poll for it (no MPI / torch needed)
+void rendezvous(const std::string& path, int rank, uint8_t id[128]) {
+    if (rank == 0) {
+        if (wafer_nccl_unique_id(id) != WAFER_OK) throw std::runtime_error(std::string("wafer_nccl_unique_id: ") + wafer_last_error(nullptr));
+        const std::string tmp = path + ".tmp";
+        FILE* f = fopen(tmp.c_str(), "wb");
+        if (!f || fwrite(id, 1, 128, f) != 128) throw std::runtime_error("rendezvous: cannot write " + tmp);
+        fclose(f);
+        rename(tmp.c_str(), path.c_str());
+    } else {
+        for (int tries = 0; tries < 600; ++tries) {
+            FILE* f = fopen(path.c_str(), "rb");
+            if (f) {
+                const size_t n = fread(id, 1, 128, f);
+                fclose(f);
+                if (n == 128) return;
+            }
+            std::this_thread::sleep_for(std::chrono::milliseconds(100));
+        }
+        throw std::runtime_error("rendezvous: timed out waiting for " + path);
+    }
+}
+
+int env_int(const char* k, int dflt) {
+    const char* v = getenv(k);
+    return v ? atoi(v) : dflt;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+    std::string config_file = "wafer.yaml", script = "gen_potential.py", outroot = "output", rdv;
+    bool check_only = false, no_output = false, quiet = false;
+    int verbosity = 0;
+    for (int i = 1; i < argc; ++i) {
+        const std::string a = argv[i];
+        auto next = [&]() -> std::string {
+            if (i + 1 >= argc) { fprintf(stderr, "missing value for %s\n", a.c_str()); exit(2); }
+            return argv[++i];
+        };
+        if (a == "-c" || a == "--config") config_file = next();
+        else if (a == "-s" || a == "--script") script = next();
+        else if (a == "-d" || a == "-dd" || a == "-ddd") verbosity += (int)a.size() - 1;
+        else if (a == "--check-config") check_only = true;
+        else if (a == "--no-output") no_output = true;
+        else if (a == "--output-root") outroot = next();
+        else if (a == "--rendezvous-file") rdv = next();
+        else if (a == "-q" || a == "--quiet") quiet = true;
+        else if (a == "-h" || a == "--help") {
+            puts("wafer-b200 [-c wafer.yaml] [-s gen_potential.py] [-d] [--check-config] [--no-output] [--output-root DIR] [-q]");
+            return 0;
+        } else { fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
+    }
+    (void)verbosity;
+    try {
+        Run r;
+        r.cfg = load_config_file(config_file);
+        r.quiet = quiet;
+        if (r.cfg.potential == 13) r.cfg.script_location = "./" + script;  // config.rs:344-350
+        if (check_only) {
+            puts(config_json(r.cfg).c_str());
+            return 0;
+        }
+        const Config& c = r.cfg;
+        if (c.init_symmetry != 0)
+            throw std::runtime_error("init_symmetry other than NotConstrained is not supported (the reference's routine "
+                                     "hard-codes the SevenPoint padding, config.rs:702-723)");
+        r.rank = env_int("RANK", 0);
+        r.world = env_int("WORLD_SIZE", 1);
+        uint8_t id[128];
+        if (r.world > 1) rendezvous(rdv.empty() ? "/tmp/wafer_b200_nccl_id_" + std::to_string(getppid()) : rdv, r.rank, id);
+        if (!no_output && r.rank == 0) {
+            // output::check_output_dir (output.rs:680-745): ./output/<project>_<date>/ + a copy of the configuration
+            char date[64];
+            const time_t now = time(nullptr);
+            strftime(date, sizeof date, "%Y-%m-%d_%H:%M:%S", localtime(&now));
+            mkdir(outroot.c_str(), 0755);
+            r.outdir = outroot + "/" + c.project_name + "_" + date;
+            mkdir(r.outdir.c_str(), 0755);
+            std::ifstream src(config_file, std::ios::binary);
+            std::ofstream dst(r.outdir + "/wafer.yaml", std::ios::binary);
+            dst << src.rdbuf();
+        }
+        wafer_params p{};
+        p.nx = c.nx; p.ny = c.ny; p.nz = c.nz; p.ext = (uint32_t)c.ext();
+        p.dn = c.dn; p.dt = c.dt; p.mass = c.mass;
+        p.device = env_int("LOCAL_RANK", -1);
+        p.rank = (uint32_t)r.rank; p.world = (uint32_t)r.world; p.nccl_id = r.world > 1 ? id : nullptr;
+        p.max_lower = c.wavemax;
+        if (wafer_create(&p, &r.ctx) != WAFER_OK) throw std::runtime_error(std::string("wafer_create: ") + wafer_last_error(nullptr));
+        const Dims d(c);
+        const auto t0 = std::chrono::steady_clock::now();
+
+        // potential::load_arrays (potential.rs:75-175)
+        if (c.potential == 12) {  // FromFile
+            std::vector<double> v(d.padded());
+            if (!read_csv_work("input/potential.csv", v, d)) throw std::runtime_error("LoadPotential: input/potential.csv not found");
+            r.ck(wafer_set_potential(r.ctx, v.data()), "wafer_set_potential");
+        } else if (c.potential == 13) {  // FromScript
+            std::vector<double> v(d.padded());
+            script_potential(c, v, d);
+            r.ck(wafer_set_potential(r.ctx, v.data()), "wafer_set_potential");
+        } else {
+            r.ck(wafer_generate_potential(r.ctx, c.potential, c.sig), "wafer_generate_potential");
+        }
+        if (c.potential == 8) {  // FullCornell: variable pot_sub (potential.rs:134-144)
+            const std::vector<double> ps = full_cornell_pot_sub(c);
+            r.ck(wafer_set_pot_sub_array(r.ctx, ps.data()), "wafer_set_pot_sub_array");
+        } else {                 // potential.rs:346-363
+            const double ps = c.potential == 6 ? 1. / c.dn : (c.potential == 7 ? 4.0 * c.mass : 0.0);
+            r.ck(wafer_set_pot_sub_scalar(r.ctx, ps), "wafer_set_pot_sub_scalar");
+        }
+        if (c.save_potential && !r.outdir.empty() && r.rank == 0) {  // potential.rs:163-172
+            std::vector<double> v(d.padded());
+            r.ck(wafer_get_potential(r.ctx, v.data()), "wafer_get_potential");
+            if (r.world == 1) write_csv_work(r.outdir + "/potential.csv", v.data(), d);
+        }
+
+        // run (grid.rs:31-47): lower states from ./input when starting above the ground state
+        for (unsigned w = 0; w < c.wavenum; ++w) {  // input::load_wavefunctions (input.rs:487-505)
+            std::vector<double> q(d.padded());
+            if (!read_csv_work("input/wavefunction_" + std::to_string(w) + ".csv", q, d))
+                throw std::runtime_error("LoadWavefunction: input/wavefunction_" + std::to_string(w) + ".csv is required when wavenum > 0");
+            r.ck(wafer_push_lower(r.ctx, q.data()), "wafer_push_lower");
+        }
+        // config::set_initial_conditions (config.rs:577-627)
+        if (c.wavenum == 0) {
+            if (c.init_condition == 0) {
+                std::vector<double> phi(d.padded());
+                if (!read_csv_work("input/wavefunction_0.csv", phi, d)) throw std::runtime_error("LoadWavefunction: input/wavefunction_0.csv not found");
+                r.ck(wafer_set_phi(r.ctx, phi.data()), "wafer_set_phi");
+            } else if (c.init_condition == 1) {  // Gaussian (config.rs:636-642): thread_rng there, so any seed is as good
+                std::vector<double> phi(d.padded(), 0.0);
+                std::mt19937_64 gen(std::random_device{}());
+                std::normal_distribution<double> normal(0.0, c.sig);
+                for (size_t i = 0; i < d.nx; ++i)
+                    for (size_t j = 0; j < d.ny; ++j)
+                        for (size_t k = 0; k < d.nz; ++k) phi[d.p(i + d.e, j + d.e, k + d.e)] = normal(gen);
+                r.ck(wafer_set_phi(r.ctx, phi.data()), "wafer_set_phi");
+            } else {
+                r.ck(wafer_generate_initial_condition(r.ctx, c.init_condition), "wafer_generate_initial_condition");
+            }
+        }
+        int rc = 0;
+        for (unsigned wnum = c.wavenum; wnum <= c.wavemax; ++wnum) {
+            if (!solve(r, wnum)) {  // Err(MaxStep) aborts the remaining states (grid.rs:44, 244)
+                fprintf(stderr, "Error: Maximum step limit reached before convergence of state %u\n", wnum);
+                rc = 1;
+                break;
+            }
+        }
+        wafer_synchronize(r.ctx);
+        if (!quiet && r.rank == 0) {
+            const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            printf("Simulation complete. Elapsed time: %.3fs; %llu kernel launches; sweep variant %s\n", s,
+                   (unsigned long long)wafer_kernel_launches(r.ctx), wafer_sweep_variant(r.ctx));
+        }
+        wafer_destroy(r.ctx);
+        return rc;
+    } catch (const std::exception& e) {
+        fprintf(stderr, "Error: %s\n", e.what());
+        return 1;
+    }
+}
