@@ -99,6 +99,9 @@ int wafer_push_lower(wafer_ctx *ctx, const double *q_padded);     /* input::load
 int wafer_push_lower_from_phi(wafer_ctx *ctx);                    /* w_store.push(phi)          (grid.rs:241)                */
 int wafer_get_lower(wafer_ctx *ctx, uint32_t idx, double *q_padded);
 int wafer_phi_from_lower(wafer_ctx *ctx, uint32_t idx);           /* phi = w_store[idx].clone() (grid.rs:95)                 */
+/* Deterministic stand-in for the clone: phi = w_store[idx] * f(x,y,z), f a fixed polynomial without symmetry.
+   The reference's clone start only works through rounding noise; see generators.cuh seed_poly. */
+int wafer_phi_seed_from_lower(wafer_ctx *ctx, uint32_t idx);
 int wafer_clear_lowers(wafer_ctx *ctx);
 uint32_t wafer_num_lowers(const wafer_ctx *ctx);
 

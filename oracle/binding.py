@@ -85,6 +85,7 @@ def lib():
         L.wo_zero_ring.argtypes = [gp, _dp]
         L.wo_initial_condition.restype = C.c_int
         L.wo_initial_condition.argtypes = [gp, C.c_int, _dp]
+        L.wo_seed_from_state.argtypes = [gp, _dp, _dp]
         L.wo_solve.restype = C.c_int
         L.wo_solve.argtypes = [gp, _dp, _dp, _dp, C.c_int, C.c_double, _dp, _dp, C.POINTER(_dp), C.c_uint32,
                                C.c_double, C.c_int64, C.c_uint64, C.c_uint64, C.POINTER(Record), C.c_uint64,
@@ -216,6 +217,13 @@ def initial_condition(g, kind):
     rc = lib().wo_initial_condition(C.byref(g), INITIAL_CONDITIONS[kind], _p(w))
     if rc:
         raise ValueError("initial condition %r is not reproducible in the oracle" % (kind,))
+    return w
+
+
+def seed_from_state(g, q):
+    """the product driver's deterministic excited-state start (generators.cuh seed_poly)"""
+    w = np.zeros(g.padded_shape)
+    lib().wo_seed_from_state(C.byref(g), _p(q), _p(w))
     return w
 
 

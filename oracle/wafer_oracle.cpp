@@ -593,6 +593,30 @@ int wo_initial_condition(const wo_grid* g, int kind, double* w) {
     return 0;
 }
 
+// Deterministic excited-state seed used by the product's driver instead of the reference's noise-seeded clone
+// (grid.rs:95): w = q * f(u,v,w).  Restated here so that whole excited-state runs can be compared.
+void wo_seed_from_state(const wo_grid* g, const double* q, double* w) {
+    const Dims d(g);
+    std::memset(w, 0, d.padded() * sizeof(double));
+    for (size_t i = 0; i < d.nx; ++i)
+        for (size_t j = 0; j < d.ny; ++j)
+            for (size_t k = 0; k < d.nz; ++k) {
+                const double u = (2. * (double)i - ((double)d.nx - 1.)) / (double)d.nx;
+                const double v = (2. * (double)j - ((double)d.ny - 1.)) / (double)d.ny;
+                const double ww = (2. * (double)k - ((double)d.nz - 1.)) / (double)d.nz;
+                double f = 1. + u;
+                f = f + 0.5 * v;
+                f = f + 0.25 * ww;
+                f = f + 0.7 * (u * v);
+                f = f + 0.4 * (v * ww);
+                f = f + 0.3 * (u * ww);
+                f = f + 0.2 * (u * u);
+                f = f - 0.1 * (v * v);
+                const size_t c = d.p(i + d.e, j + d.e, k + d.e);
+                w[c] = q[c] * f;
+            }
+}
+
 // ---------------------------------------------------------------- grid.rs:50-246
 // phi: in = initial condition (set_initial_conditions result, or a seed / clone of w_store[wnum-1]);
 //      out = state at loop exit.  max_steps < 0 means None; snap_update == 0 means None.

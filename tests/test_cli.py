@@ -93,6 +93,14 @@ def test_default_run_matches_oracle(binary, oracle, tmp_path):
     got = wf[:, 3].reshape(50, 50, 50)
     ref_work = phi[1:-1, 1:-1, 1:-1]
     assert np.linalg.norm(got - ref_work) / np.linalg.norm(ref_work) < 1e-8
+    # first excited state: the driver seeds it deterministically (generators.cuh seed_poly), so it is comparable
     assert (outdir / "observables_1.json").exists() and (outdir / "wavefunction_1.csv").exists()
+    lowers = [phi]
+    p1 = oracle.seed_from_state(g, phi)
+    conv1, rec1 = oracle.solve(g, v, a, b, p1, lowers=lowers, tolerance=1e-4, screen_update=1000, max_records=400)
+    assert conv1
     e1 = json.loads((outdir / "observables_1.json").read_text())["energy"]
-    assert e1 > obs["energy"]
+    assert e1 == pytest.approx(rec1[-1]["E"], rel=1e-9) and e1 > obs["energy"]
+    assert len(rows) == 19 + len(rec1)
+    wf1 = np.loadtxt(outdir / "wavefunction_1.csv", delimiter=",")[:, 3].reshape(50, 50, 50)
+    assert np.linalg.norm(wf1 - p1[1:-1, 1:-1, 1:-1]) / np.linalg.norm(p1[1:-1, 1:-1, 1:-1]) < 1e-8

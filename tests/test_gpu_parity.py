@@ -399,6 +399,16 @@ def test_excited_states_with_deterministic_seeds(wb, oracle):
     assert e_ref[2] == pytest.approx(e_ref[1], abs=1e-6)  # degenerate shell
 
 
+def test_excited_state_seed_matches_restatement(wb, oracle):
+    g = oracle.make_grid(13, 10, 12, ext=2, dn=0.1, dt=1e-3, mass=1.0)
+    q = np.zeros(g.padded_shape)
+    npr.work(q, 2)[...] = np.random.default_rng(2).normal(size=g.work_shape)
+    with wb.Lattice((13, 10, 12), "FivePoint") as lat:
+        lat.push_lower(q)
+        lat.phi_seed_from_lower(0)
+        assert np.array_equal(lat.get_phi(), oracle.seed_from_state(g, q))
+
+
 def test_max_steps_and_snapshot_semantics(wb, oracle):
     g = oracle.make_grid(8, 8, 8, ext=1, dn=0.1, dt=1e-3, mass=1.0)
     v = oracle.potential(g, "Harmonic")

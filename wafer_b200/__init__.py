@@ -232,6 +232,10 @@ class Lattice:
     def phi_from_lower(self, idx):
         self._ck(self._lib.wafer_phi_from_lower(self._h, idx))
 
+    def phi_seed_from_lower(self, idx):
+        """deterministic excited-state start: phi = w_store[idx] * seed polynomial (see generators.cuh)"""
+        self._ck(self._lib.wafer_phi_seed_from_lower(self._h, idx))
+
     def clear_lowers(self):
         self._ck(self._lib.wafer_clear_lowers(self._h))
 

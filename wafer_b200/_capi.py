@@ -46,6 +46,7 @@ SYMBOLS = {
     "wafer_push_lower_from_phi": (C.c_int, [_ctx]),
     "wafer_get_lower": (C.c_int, [_ctx, C.c_uint32, _dp]),
     "wafer_phi_from_lower": (C.c_int, [_ctx, C.c_uint32]),
+    "wafer_phi_seed_from_lower": (C.c_int, [_ctx, C.c_uint32]),
     "wafer_clear_lowers": (C.c_int, [_ctx]),
     "wafer_num_lowers": (C.c_uint32, [_ctx]),
     "wafer_generate_potential": (C.c_int, [_ctx, C.c_int32, C.c_double]),

@@ -204,4 +204,37 @@ __global__ void __launch_bounds__(128) gen_ic_kernel(double* __restrict__ w, Geo
     }
 }
 
+
+// Deterministic excited-state start.  The reference starts state n > 0 from a clone of state n-1 (grid.rs:95) and
+// relies on the ~1e-16 rounding residue that survives the first normalise + Gram-Schmidt to seed the new state
+// (SURVEY F7); when the sums happen to round exactly (they do on this implementation) the residue is exactly zero
+// and the next step divides 0 by 0.  seed = q * f(u,v,w) with a fixed polynomial without any symmetry,
+// u,v,w in [-1,1] across the lattice; plain IEEE +,-,*,/ in a fixed order, so a host restatement is bit-identical.
+__device__ __host__ inline double seed_poly(long long gi, long long gj, long long gk, long long nx, long long ny, long long nz) {
+    const double u = (2. * (double)gi - ((double)nx - 1.)) / (double)nx;
+    const double v = (2. * (double)gj - ((double)ny - 1.)) / (double)ny;
+    const double w = (2. * (double)gk - ((double)nz - 1.)) / (double)nz;
+    double f = 1. + u;
+    f = f + 0.5 * v;
+    f = f + 0.25 * w;
+    f = f + 0.7 * (u * v);
+    f = f + 0.4 * (v * w);
+    f = f + 0.3 * (u * w);
+    f = f + 0.2 * (u * u);
+    f = f - 0.1 * (v * v);
+    return f;
+}
+
+__global__ void __launch_bounds__(128) seed_from_state_kernel(double* __restrict__ w, const double* __restrict__ q, Geom g) {
+    const long long rows = (long long)(g.L + 2 * g.gx) * g.ny;
+    for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+        const int i = (int)(r / g.ny) - g.gx, j = (int)(r % g.ny);
+        const long long gi = g.x0 + i;
+        const long long o = g.off(i, j, 0);
+        const bool inside = gi >= 0 && gi < g.gnx;
+        for (int k = threadIdx.x; k < g.nz; k += blockDim.x)
+            w[o + k] = inside ? q[o + k] * seed_poly(gi, j, k, g.gnx, g.gny, g.gnz) : 0.0;
+    }
+}
+
 }  // namespace wafer

@@ -195,7 +195,9 @@ bool solve(Run& r, unsigned wnum) {
         if (read_csv_work("input/wavefunction_" + std::to_string(wnum) + ".csv", phi, d)) {
             r.ck(wafer_set_phi(r.ctx, phi.data()), "wafer_set_phi");
         } else {
-            r.ck(wafer_phi_from_lower(r.ctx, wnum - 1), "wafer_phi_from_lower");
+            // grid.rs:95 clones w_store[wnum-1] and lets rounding noise seed the new state; here the
+            // clone is multiplied by a fixed symmetry-free polynomial so the start is well defined and reproducible
+            r.ck(wafer_phi_seed_from_lower(r.ctx, wnum - 1), "wafer_phi_seed_from_lower");
         }
     }
     if (!r.quiet && r.rank == 0) {

@@ -646,6 +646,18 @@ int wafer_phi_from_lower(wafer_ctx* ctx, uint32_t idx) {
     return WAFER_OK;
 }
 
+int wafer_phi_seed_from_lower(wafer_ctx* ctx, uint32_t idx) {
+    if (!ctx) return WAFER_ERR_INVALID;
+    REQUIRE(idx < ctx->lowers.size(), "no such lower state");
+    CK(cudaSetDevice(ctx->dev));
+    const long long rows = (long long)(ctx->g.L + 2 * ctx->g.gx) * ctx->g.ny;
+    seed_from_state_kernel<<<(int)std::min<long long>(rows, (long long)ctx->sm_count * 32), 128, 0, ctx->s_main>>>(
+        ctx->psi[ctx->cur], ctx->lowers[idx], ctx->g);
+    TRY(post_launch(ctx));
+    ctx->have_phi = true;
+    return WAFER_OK;
+}
+
 int wafer_clear_lowers(wafer_ctx* ctx) {
     if (!ctx) return WAFER_ERR_INVALID;
     CK(cudaSetDevice(ctx->dev));
