@@ -135,6 +135,13 @@ int wafer_host_alloc(void **ptr, size_t bytes);        /* pinned host memory for
 int wafer_host_free(void *ptr);
 int wafer_device_info(const wafer_ctx *ctx, char *name, size_t name_len, int32_t *sm_count, int32_t *cc_major,
                       int32_t *cc_minor, uint64_t *mem_bytes);
+/* Fused halo exchange over NVLink peer memory (optional, world > 1).  Every rank exports 192 bytes (CUDA IPC handles of
+   its two psi buffers and its flag words), the host ships rank r-1's and rank r+1's blobs to rank r (NULL at the ends of
+   the chain) and calls connect.  From then on the boundary-plane launches of wafer_evolve store their results directly
+   into the neighbours' ghost planes and ranks order themselves with flag words in peer memory; without it the same
+   planes travel by ncclSend/ncclRecv. */
+int wafer_p2p_export(wafer_ctx *ctx, uint8_t out[192]);
+int wafer_p2p_connect(wafer_ctx *ctx, const uint8_t *lower, const uint8_t *upper);
 /* self-test of the sweep's division by the loop-invariant denominator: compares it bit-for-bit with IEEE
    division on n pseudo-random operands (every exponent, zeros, denormals, NaN/Inf); *mismatches must be 0 */
 int wafer_selftest_division(wafer_ctx *ctx, double den, uint64_t n, uint64_t seed, uint64_t *mismatches);

@@ -7,9 +7,11 @@ OUT=gpurun_out/$LABEL
 mkdir -p "$OUT"
 nvidia-smi --query-gpu=index,name,clocks.sm,clocks.max.sm,power.draw --format=csv > "$OUT/gpu.csv" 2>&1
 nvidia-smi topo -m > "$OUT/topo.txt" 2>&1
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29601 \
-    scripts/multigpu_check.py > "$OUT/multigpu_check.log" 2>&1
-echo "multigpu_check rc=$?" | tee -a "$OUT/rc.log"; grep '^{' "$OUT/multigpu_check.log" | tail -1; tail -3 "$OUT/multigpu_check.log"
+for mode in 1 0; do
+  WAFER_P2P=$mode timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29601+mode)) \
+      scripts/multigpu_check.py > "$OUT/multigpu_check_p2p$mode.log" 2>&1
+  echo "multigpu_check p2p=$mode rc=$?" | tee -a "$OUT/rc.log"; grep '^{' "$OUT/multigpu_check_p2p$mode.log" | tail -1; tail -2 "$OUT/multigpu_check_p2p$mode.log" | cut -c1-300
+done
 for n in ${NLIST:-1 2 4 8}; do
   [ $n -gt $N ] && break
   if [ $n -eq 1 ]; then

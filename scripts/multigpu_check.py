@@ -30,6 +30,15 @@ def main():
         dist.broadcast(idt, 0)
         return bytes(idt.cpu().tolist())
 
+    use_p2p = os.environ.get("WAFER_P2P", "1") == "1"
+
+    def connect(lat):
+        mine = torch.tensor(list(lat.p2p_export()), dtype=torch.uint8, device="cuda")
+        blobs = [torch.zeros(192, dtype=torch.uint8, device="cuda") for _ in range(world)]
+        dist.all_gather(blobs, mine)
+        blobs = [bytes(b.cpu().tolist()) for b in blobs]
+        lat.p2p_connect(blobs[rank - 1] if rank > 0 else None, blobs[rank + 1] if rank < world - 1 else None)
+
     results = {}
     ok = True
     for ext, cd, shape in ((1, "ThreePoint", (96, 40, 72)), (2, "FivePoint", (50, 33, 40)), (3, "SevenPoint", (41, 24, 30))):
@@ -45,11 +54,15 @@ def main():
         kw = dict(dn=dn, dt=dt, mass=mass, device=local)
         single = wafer_b200.Lattice(shape, cd, **kw)
         multi = wafer_b200.Lattice(shape, cd, rank=rank, world=world, nccl_id=fresh_nccl_id(), **kw)
+        if use_p2p:
+            connect(multi)
         outs = []
         for lat in (single, multi):
             lat.set_potential(v)
             lat.set_phi(phi)
             lat.evolve(0, 7)
+            lat.evolve(0, 3)     # odd + even tails back to back: the single-step pass must hand over depth-2 ghosts
+            lat.evolve(0, 4)
             g = lat.get_phi()    # before the check: its normalise divides by a sum whose last bit depends on the
             o1 = lat.check(0)    # reduction order (per-rank partials + all-reduce), the sweep itself does not
             lat.push_lower(q)
@@ -75,7 +88,7 @@ def main():
         single.close()
         multi.close()
     if rank == 0:
-        print(json.dumps({"world": world, "ok": ok, "results": results}), flush=True)
+        print(json.dumps({"world": world, "ok": ok, "halo": "p2p" if use_p2p else "nccl", "results": results}), flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

@@ -151,6 +151,18 @@ class Lattice:
     def sweep_variant(self):
         return self._lib.wafer_sweep_variant(self._h).decode()
 
+    def p2p_export(self):
+        """192-byte blob (CUDA IPC handles) the x-neighbours need for the fused halo path"""
+        buf = (C.c_uint8 * 192)()
+        self._ck(self._lib.wafer_p2p_export(self._h, buf))
+        return bytes(buf)
+
+    def p2p_connect(self, lower, upper):
+        """lower / upper: p2p_export() blobs of rank-1 / rank+1 (None at the ends of the chain)"""
+        lo = (C.c_uint8 * 192).from_buffer_copy(lower) if lower is not None else None
+        hi = (C.c_uint8 * 192).from_buffer_copy(upper) if upper is not None else None
+        self._ck(self._lib.wafer_p2p_connect(self._h, lo, hi))
+
     def selftest_division(self, den, n=1 << 24, seed=0):
         bad = C.c_uint64()
         self._ck(self._lib.wafer_selftest_division(self._h, den, n, seed, C.byref(bad)))

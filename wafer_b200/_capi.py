@@ -67,6 +67,8 @@ SYMBOLS = {
     "wafer_host_free": (C.c_int, [C.c_void_p]),
     "wafer_device_info": (C.c_int, [_ctx, C.c_char_p, C.c_size_t, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                     C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]),
+    "wafer_p2p_export": (C.c_int, [_ctx, C.POINTER(C.c_uint8)]),
+    "wafer_p2p_connect": (C.c_int, [_ctx, C.POINTER(C.c_uint8), C.POINTER(C.c_uint8)]),
     "wafer_selftest_division": (C.c_int, [_ctx, C.c_double, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]),
     "wafer_version": (C.c_char_p, []),
     "wafer_sweep_variant": (C.c_char_p, [_ctx]),

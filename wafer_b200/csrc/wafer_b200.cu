@@ -55,6 +55,14 @@ struct wafer_ctx {
     bool have_v = false, have_phi = false;
     uint64_t launches = 0;
     NcclComm comm = nullptr;
+    // fused halo over peer memory (CUDA IPC): neighbour 0 = rank-1 (lower x), 1 = rank+1
+    bool p2p = false;
+    double* peer_psi[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [neighbour][buffer index]
+    unsigned long long* flags = nullptr;                  // [0] written by rank-1, [1] by rank+1: passes completed
+    unsigned long long* peer_flags[2] = {nullptr, nullptr};
+    int* p2p_timeout = nullptr;                           // device flag: a wait gave up (peer died)
+    unsigned long long pass = 0;                          // boundary passes completed (same on every rank)
+    int peer_L[2] = {0, 0};
     mutable std::string err;
     size_t bytes() const { return (size_t)g.total() * sizeof(double); }
 };
@@ -192,7 +200,8 @@ int init_tb(wafer_ctx* ctx) {
     TRY(make_tensor_map(ctx, &ctx->tm_psi[0], ctx->psi[0], tb::R0));
     TRY(make_tensor_map(ctx, &ctx->tm_psi[1], ctx->psi[1], tb::R0));
     TRY(make_tensor_map(ctx, &ctx->tm_v, ctx->v, tb::R1));
-    CK(cudaFuncSetAttribute(tb::sweep_tb2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(tb::sweep_tb2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(tb::sweep_tb2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb::SMEM_BYTES));
     const double den = denominator(ctx);
     ctx->den_ok = (den > 7.888609052210118e-31 && den < 1.2676506002282294e30) ? 1 : 0;  // 2^-100 .. 2^100
     // x chunk: enough CTAs for ~8 waves, at most 128 planes (pipeline fill is 4 planes per chunk)
@@ -204,15 +213,50 @@ int init_tb(wafer_ctx* ctx) {
     return WAFER_OK;
 }
 
-// two lattice steps: psi[src] -> psi[src^1] for planes [xb, xe)
-int launch_sweep_tb2(wafer_ctx* ctx, int src, int xb, int xe, cudaStream_t st) {
+// two lattice steps: psi[src] -> psi[src^1] for planes [xb, xe); peer != nullptr: also store every output at the
+// same (plane + peer_plane_shift, row, column) of the neighbour's buffer `peer`
+int launch_sweep_tb2(wafer_ctx* ctx, int src, int xb, int xe, cudaStream_t st, double* peer = nullptr,
+                     long long peer_plane_shift = 0) {
     if (xe <= xb) return WAFER_OK;
     const Geom& g = ctx->g;
     const int chunk = std::min(ctx->tb_xchunk, std::max(xe - xb, 1));
     dim3 grid(ceil_div(g.nz, tb::TZ), ceil_div(g.ny, tb::TY), ceil_div(xe - xb, chunk));
-    tb::sweep_tb2_kernel<<<grid, tb::THREADS, tb::SMEM_BYTES, st>>>(ctx->tm_psi[src], ctx->tm_v, ctx->psi[src ^ 1], g, xb, xe,
-                                                                    chunk, ctx->p.dt, denominator(ctx), ctx->den_ok);
+    double* out = ctx->psi[src ^ 1];
+    if (peer) {
+        const long long delta = (peer - out) + peer_plane_shift * g.plane;  // element distance local site -> peer site
+        tb::sweep_tb2_kernel<true><<<grid, tb::THREADS, tb::SMEM_BYTES, st>>>(ctx->tm_psi[src], ctx->tm_v, out, delta, g, xb, xe, chunk,
+                                                                              ctx->p.dt, denominator(ctx), ctx->den_ok);
+    } else {
+        tb::sweep_tb2_kernel<false><<<grid, tb::THREADS, tb::SMEM_BYTES, st>>>(ctx->tm_psi[src], ctx->tm_v, out, 0, g, xb, xe, chunk,
+                                                                               ctx->p.dt, denominator(ctx), ctx->den_ok);
+    }
     return post_launch(ctx);
+}
+
+// ---- inter-GPU ordering for the fused halo: monotone pass counters in peer-visible memory ------------------
+// flags[0] is written by rank-1, flags[1] by rank+1 ("my boundary planes of pass n are in your ghost planes and I
+// no longer read the ghost planes you are about to overwrite").  Spins are bounded (~30 s) so a dead peer cannot
+// hang the GPU.
+__global__ void p2p_wait_kernel(const volatile unsigned long long* flags, unsigned long long need, int has_lo, int has_hi,
+                                int* timeout_flag) {
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+    for (int n = 0; n < 2; ++n) {
+        if (!(n == 0 ? has_lo : has_hi)) continue;
+        while (flags[n] < need) {
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 30000000000ull) { *timeout_flag = 1; return; }
+            __nanosleep(200);
+        }
+    }
+    __threadfence_system();  // acquire: the neighbour's ghost-plane stores precede its flag store
+}
+__global__ void p2p_signal_kernel(volatile unsigned long long* peer_lo, volatile unsigned long long* peer_hi,
+                                  unsigned long long value) {
+    __threadfence_system();  // release: every store of the preceding kernels in this stream (incl. peer stores)
+    if (peer_lo) peer_lo[1] = value;  // I am rank-1's upper neighbour
+    if (peer_hi) peer_hi[0] = value;  // I am rank+1's lower neighbour
+    __threadfence_system();
 }
 
 // ghost-plane halo exchange of `buf` with the x neighbours (NCCL send/recv over NVLink)
@@ -483,6 +527,12 @@ int wafer_destroy(wafer_ctx* ctx) {
     if (ctx->s_main) cudaStreamSynchronize(ctx->s_main);
     if (ctx->s_halo) cudaStreamSynchronize(ctx->s_halo);
     if (ctx->comm) nccl_api().CommDestroy(ctx->comm);
+    for (int n = 0; n < 2; ++n) {
+        if (ctx->peer_psi[n][0]) cudaIpcCloseMemHandle(ctx->peer_psi[n][0]);
+        if (ctx->peer_psi[n][1]) cudaIpcCloseMemHandle(ctx->peer_psi[n][1]);
+        if (ctx->peer_flags[n]) cudaIpcCloseMemHandle(ctx->peer_flags[n]);
+    }
+    cudaFree(ctx->flags); cudaFree(ctx->p2p_timeout);
     for (double* q : ctx->lowers) cudaFree(q);
     cudaFree(ctx->psi[0]); cudaFree(ctx->psi[1]); cudaFree(ctx->v); cudaFree(ctx->a); cudaFree(ctx->b);
     cudaFree(ctx->staging); cudaFree(ctx->potsub_arr); cudaFree(ctx->partials); cudaFree(ctx->scal); cudaFree(ctx->ring_flag);
@@ -759,27 +809,49 @@ int wafer_evolve(wafer_ctx* ctx, uint8_t wnum_in, uint64_t steps) {
         CK(cudaEventRecord(ctx->ev_halo, ctx->s_main));
     }
     const uint64_t total = steps == 0 ? 1 : steps;  // grid.rs:562-686 is a do-while: steps == 0 still sweeps once
+    const bool fused = overlap && ctx->p2p;  // halo stores fused into the boundary kernels (peer memory), no NCCL
+    const int has_lo = ctx->rank > 0, has_hi = ctx->rank < ctx->world - 1;
     uint64_t done = 0;
     while (done < total) {
         // ground state: two steps per HBM pass with the time-tiled TMA kernel whenever two steps remain;
         // excited states need a global norm / Gram-Schmidt after EVERY step (grid.rs:674-681): one step per pass
         const bool two = ctx->use_tb && !excited && total - done >= 2;
-        const int b = two ? 2 : g.e;  // boundary planes whose new values the neighbours need
+        const int b = g.gx;  // boundary planes = ghost depth the neighbours keep (2 for ThreePoint, else ext)
         const int src = ctx->cur;
         const double* cur = ctx->psi[src];
         double* nxt = ctx->psi[src ^ 1];
         if (overlap) {
-            // boundary planes + NVLink halo exchange on the high-priority stream, interior on the main stream
+            // boundary planes + halo on the high-priority stream, interior on the main stream
             CK(cudaStreamWaitEvent(ctx->s_halo, ctx->ev_main, 0));
             CK(cudaStreamWaitEvent(ctx->s_main, ctx->ev_halo, 0));
+            if (fused) {
+                // my ghost planes of `cur` hold the neighbours' pass-(n-1) boundary planes once their flag says so;
+                // the same flag says they are done reading the ghost planes (of their `nxt`) that I overwrite now
+                p2p_wait_kernel<<<1, 1, 0, ctx->s_halo>>>(ctx->flags, ctx->pass, has_lo, has_hi, ctx->p2p_timeout);
+                TRY(post_launch(ctx));
+            }
+            double* plo = fused && has_lo ? ctx->peer_psi[0][src ^ 1] : nullptr;
+            double* phi_ = fused && has_hi ? ctx->peer_psi[1][src ^ 1] : nullptr;
             if (two) {
-                TRY(launch_sweep_tb2(ctx, src, 0, b, ctx->s_halo));
-                TRY(launch_sweep_tb2(ctx, src, g.L - b, g.L, ctx->s_halo));
+                // my planes [0,b) are the lower neighbour's ghost planes [L_lo, L_lo+b); my [L-b,L) the upper one's [-b,0)
+                TRY(launch_sweep_tb2(ctx, src, 0, b, ctx->s_halo, plo, ctx->peer_L[0]));
+                TRY(launch_sweep_tb2(ctx, src, g.L - b, g.L, ctx->s_halo, phi_, -(long long)g.L));
             } else {
                 TRY(launch_sweep(ctx, cur, nxt, 0, b, false, 0, ctx->s_halo));
                 TRY(launch_sweep(ctx, cur, nxt, g.L - b, g.L, false, 0, ctx->s_halo));
+                if (fused) {  // rare odd tail step: plain peer copies of the boundary planes
+                    const size_t bytes = (size_t)b * g.plane * sizeof(double);
+                    if (plo) CK(cudaMemcpyAsync(plo + g.off(ctx->peer_L[0], -g.e, 0), nxt + g.off(0, -g.e, 0), bytes, cudaMemcpyDeviceToDevice, ctx->s_halo));
+                    if (phi_) CK(cudaMemcpyAsync(phi_ + g.off(-b, -g.e, 0), nxt + g.off(g.L - b, -g.e, 0), bytes, cudaMemcpyDeviceToDevice, ctx->s_halo));
+                }
             }
-            TRY(exchange(ctx, nxt, ctx->s_halo));
+            if (fused) {
+                ctx->pass += 1;
+                p2p_signal_kernel<<<1, 1, 0, ctx->s_halo>>>(has_lo ? ctx->peer_flags[0] : nullptr, has_hi ? ctx->peer_flags[1] : nullptr, ctx->pass);
+                TRY(post_launch(ctx));
+            } else {
+                TRY(exchange(ctx, nxt, ctx->s_halo));
+            }
             CK(cudaEventRecord(ctx->ev_halo, ctx->s_halo));
             if (two) TRY(launch_sweep_tb2(ctx, src, b, g.L - b, ctx->s_main));
             else TRY(launch_sweep(ctx, cur, nxt, b, g.L - b, false, 0, ctx->s_main));
@@ -859,6 +931,11 @@ int wafer_synchronize(wafer_ctx* ctx) {
     CK(cudaSetDevice(ctx->dev));
     CK(cudaStreamSynchronize(ctx->s_halo));
     CK(cudaStreamSynchronize(ctx->s_main));
+    if (ctx->p2p_timeout) {
+        int t = 0;
+        CK(cudaMemcpy(&t, ctx->p2p_timeout, sizeof(int), cudaMemcpyDeviceToHost));
+        if (t) { ctx->err = "fused halo: timed out waiting for a neighbour GPU's pass flag"; return WAFER_ERR_NCCL; }
+    }
     return WAFER_OK;
 }
 
@@ -903,6 +980,52 @@ int wafer_device_info(const wafer_ctx* ctx, char* name, size_t name_len, int32_t
     return WAFER_OK;
 }
 
+// ---- fused halo over peer memory: export / import CUDA IPC handles of the psi buffers and the flag words ------
+int wafer_p2p_export(wafer_ctx* ctx, uint8_t out[192]) {
+    if (!ctx) return WAFER_ERR_INVALID;
+    REQUIRE(out, "out is NULL");
+    CK(cudaSetDevice(ctx->dev));
+    if (!ctx->flags) {
+        CK(cudaMalloc(&ctx->flags, 2 * sizeof(unsigned long long)));
+        CK(cudaMemset(ctx->flags, 0, 2 * sizeof(unsigned long long)));
+        CK(cudaMalloc(&ctx->p2p_timeout, sizeof(int)));
+        CK(cudaMemset(ctx->p2p_timeout, 0, sizeof(int)));
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h[3];
+    CK(cudaIpcGetMemHandle(&h[0], ctx->psi[0]));
+    CK(cudaIpcGetMemHandle(&h[1], ctx->psi[1]));
+    CK(cudaIpcGetMemHandle(&h[2], ctx->flags));
+    memcpy(out, h, 192);
+    return WAFER_OK;
+}
+
+int wafer_p2p_connect(wafer_ctx* ctx, const uint8_t* lower, const uint8_t* upper) {
+    if (!ctx) return WAFER_ERR_INVALID;
+    REQUIRE(ctx->world > 1, "wafer_p2p_connect needs world > 1");
+    REQUIRE(ctx->flags, "call wafer_p2p_export first");
+    REQUIRE((ctx->rank == 0) == (lower == nullptr) && (ctx->rank == ctx->world - 1) == (upper == nullptr),
+            "pass the export blobs of rank-1 and rank+1 (NULL at the ends of the chain)");
+    CK(cudaSetDevice(ctx->dev));
+    const uint8_t* blobs[2] = {lower, upper};
+    for (int n = 0; n < 2; ++n) {
+        if (!blobs[n]) continue;
+        cudaIpcMemHandle_t h[3];
+        memcpy(h, blobs[n], 192);
+        void* p[3];
+        for (int k = 0; k < 3; ++k) CK(cudaIpcOpenMemHandle(&p[k], h[k], cudaIpcMemLazyEnablePeerAccess));
+        ctx->peer_psi[n][0] = (double*)p[0];
+        ctx->peer_psi[n][1] = (double*)p[1];
+        ctx->peer_flags[n] = (unsigned long long*)p[2];
+        uint64_t x0, x1;
+        wafer_slab_partition(ctx->p.nx, (uint32_t)ctx->world, (uint32_t)(ctx->rank + (n == 0 ? -1 : 1)), &x0, &x1);
+        ctx->peer_L[n] = (int)(x1 - x0);
+    }
+    ctx->p2p = true;
+    ctx->pass = 0;
+    return WAFER_OK;
+}
+
 int wafer_selftest_division(wafer_ctx* ctx, double den, uint64_t n, uint64_t seed, uint64_t* mismatches) {
     if (!ctx) return WAFER_ERR_INVALID;
     REQUIRE(mismatches, "mismatches is NULL");
@@ -923,7 +1046,7 @@ int wafer_selftest_division(wafer_ctx* ctx, double den, uint64_t n, uint64_t see
 
 const char* wafer_sweep_variant(const wafer_ctx* ctx) {
     if (!ctx) return "";
-    if (ctx->use_tb) return "tb2-tma/V-onfly";
+    if (ctx->use_tb) return ctx->p2p ? "tb2-tma/V-onfly+p2p-halo" : "tb2-tma/V-onfly";
     return ctx->onfly ? "simple-regqueue/V-onfly" : "simple-regqueue/AB-arrays";
 }
 
