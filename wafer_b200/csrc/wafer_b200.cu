@@ -219,8 +219,18 @@ int launch_sweep_tb2(wafer_ctx* ctx, int src, int xb, int xe, cudaStream_t st, d
                      long long peer_plane_shift = 0) {
     if (xe <= xb) return WAFER_OK;
     const Geom& g = ctx->g;
-    const int chunk = std::min(ctx->tb_xchunk, std::max(xe - xb, 1));
-    dim3 grid(ceil_div(g.nz, tb::TZ), ceil_div(g.ny, tb::TY), ceil_div(xe - xb, chunk));
+    // x chunking: every chunk pays ~3 plane-iterations of pipeline fill, and CTAs run in waves of one per SM.
+    // Pick the chunk count that minimises  waves(tiles * nc) * (planes / nc + fill).
+    const long long tiles = (long long)ceil_div(g.nz, tb::TZ) * ceil_div(g.ny, tb::TY);
+    const int planes = xe - xb, slots = ctx->sm_count * tb::CTAS_PER_SM;
+    int best_nc = 1;
+    double best_cost = 1e300;
+    for (int nc = 1; nc <= std::min(planes, 64); ++nc) {
+        const double cost = (double)ceil_div(tiles * nc, slots) * ((double)ceil_div(planes, nc) + 3.0);
+        if (cost < best_cost * 0.999) { best_cost = cost; best_nc = nc; }
+    }
+    const int chunk = ceil_div(planes, best_nc);
+    dim3 grid(ceil_div(g.nz, tb::TZ), ceil_div(g.ny, tb::TY), ceil_div(planes, chunk));
     double* out = ctx->psi[src ^ 1];
     if (peer) {
         const long long delta = (peer - out) + peer_plane_shift * g.plane;  // element distance local site -> peer site
