@@ -25,6 +25,7 @@
 
 #include "../../../include/wafer_b200.h"
 #include "config.hpp"
+#include "formats.hpp"
 
 using namespace wafer_host;
 
@@ -47,35 +48,17 @@ std::string ordinal(unsigned n) {
     return std::to_string(n) + suf;
 }
 
-// ---- plain csv arrays: rows `i,j,k,data` over the WORK area, x-major / z fastest, no header (output.rs:148-166) ----
-void write_csv_work(const std::string& path, const double* padded, const Dims& d) {
-    FILE* f = fopen(path.c_str(), "w");
-    if (!f) throw std::runtime_error("CreateFile: " + path);
-    for (size_t i = 0; i < d.nx; ++i)
-        for (size_t j = 0; j < d.ny; ++j)
-            for (size_t k = 0; k < d.nz; ++k)
-                fprintf(f, "%zu,%zu,%zu,%.17g\n", i, j, k, padded[d.p(i + d.e, j + d.e, k + d.e)]);
-    fclose(f);
+// array files: work area out (output.rs:79-216), work area in with optional trilinear resize (input.rs:149-176)
+void write_work(const std::string& stem, int file_type, const double* padded, const Dims& d) {
+    write_array(stem, file_type, extract_work(padded, d.nx, d.ny, d.nz, d.e));
 }
-
-// input.rs:607-662 without the trilinear resize: the file must have the configured work size
-bool read_csv_work(const std::string& path, std::vector<double>& padded, const Dims& d) {
-    std::ifstream f(path);
-    if (!f) return false;
-    std::fill(padded.begin(), padded.end(), 0.0);
-    std::string line;
-    size_t n = 0;
-    while (std::getline(f, line)) {
-        if (line.empty()) continue;
-        size_t i, j, k;
-        double v;
-        if (sscanf(line.c_str(), "%zu,%zu,%zu,%lf", &i, &j, &k, &v) != 4) throw std::runtime_error("ParsePlainRecord: " + path);
-        if (i >= d.nx || j >= d.ny || k >= d.nz)
-            throw std::runtime_error("ArrayShape: " + path + " does not match grid.size (resizing is not supported by this build)");
-        padded[d.p(i + d.e, j + d.e, k + d.e)] = v;
-        ++n;
+bool read_work(const std::string& stem, int file_type, std::vector<double>& padded, const Dims& d) {
+    Array3 a;
+    if (!read_array(stem, file_type, a)) return false;
+    if (a.nx < 2 || a.ny < 2 || a.nz < 2) {
+        if (a.nx != d.nx || a.ny != d.ny || a.nz != d.nz) throw std::runtime_error("ArrayShape: " + stem + " cannot be resized");
     }
-    if (n != d.nx * d.ny * d.nz) throw std::runtime_error("ArrayShape: " + path + " does not match grid.size");
+    embed_work(a, padded, d.nx, d.ny, d.nz, d.e);
     return true;
 }
 
@@ -166,11 +149,20 @@ void write_observables(const Run& r, unsigned wnum, const wafer_observables& o) 
         printf("══▶ rᵣₘₛ = %.15g\n══▶ L/rᵣₘₛ = %.15g\n\n", rn, l_r);
     }
     if (r.outdir.empty() || r.rank != 0) return;
-    const bool csv = r.cfg.file_type == 1;
-    const std::string path = r.outdir + "/observables_" + std::to_string(wnum) + (csv ? ".csv" : ".json");
+    const int ft = r.cfg.file_type;
+    const std::string stem = r.outdir + "/observables_" + std::to_string(wnum);
+    if (ft == 0) {  // rmp-serde: the struct as a 5-element array (output.rs:604-620)
+        std::string o;
+        mp::put_array_header(o, 5);
+        mp::put_uint(o, wnum);
+        mp::put_f64(o, energy); mp::put_f64(o, binding); mp::put_f64(o, rn); mp::put_f64(o, l_r);
+        write_file(stem + ".mpk", o);
+        return;
+    }
+    const std::string path = stem + (ft == 1 ? ".csv" : ".json");
     FILE* f = fopen(path.c_str(), "w");
     if (!f) throw std::runtime_error("CreateFile: " + path);
-    if (csv) fprintf(f, "state,energy,binding_energy,r,l_r\n%u,%.17g,%.17g,%.17g,%.17g\n", wnum, energy, binding, rn, l_r);
+    if (ft == 1) fprintf(f, "state,energy,binding_energy,r,l_r\n%u,%.17g,%.17g,%.17g,%.17g\n", wnum, energy, binding, rn, l_r);
     else fprintf(f, "{\"state\":%u,\"energy\":%.17g,\"binding_energy\":%.17g,\"r\":%.17g,\"l_r\":%.17g}\n", wnum, energy, binding, rn, l_r);
     fclose(f);
 }
@@ -182,7 +174,7 @@ void save_wavefunction(const Run& r, unsigned wnum, bool converged) {
     r.ck(wafer_get_phi(r.ctx, phi.data()), "wafer_get_phi");
     std::string name = r.outdir + "/wavefunction_" + std::to_string(wnum) + (converged ? "" : "_partial");
     if (r.world > 1) name += ".rank" + std::to_string(r.rank);  // each rank holds (and writes) only its slab
-    write_csv_work(name + ".csv", phi.data(), d);
+    write_work(name, r.cfg.file_type, phi.data(), d);
 }
 
 // grid.rs:50-246 for one state; returns true when converged
@@ -192,7 +184,7 @@ bool solve(Run& r, unsigned wnum) {
     if (wnum > 0) {
         // grid.rs:60-96: a wavefunction_{wnum} file in ./input wins, else start from the previous converged state
         std::vector<double> phi(d.padded());
-        if (read_csv_work("input/wavefunction_" + std::to_string(wnum) + ".csv", phi, d)) {
+        if (read_work("input/wavefunction_" + std::to_string(wnum), c.file_type, phi, d)) {
             r.ck(wafer_set_phi(r.ctx, phi.data()), "wafer_set_phi");
         } else {
             // grid.rs:95 clones w_store[wnum-1] and lets rounding noise seed the new state; here the
@@ -233,7 +225,7 @@ bool solve(Run& r, unsigned wnum) {
         if (c.snap_update && !r.outdir.empty()) {                                                        // grid.rs:174-190
             std::string partial = r.outdir + "/wavefunction_" + std::to_string(wnum) + "_partial";
             if (r.world > 1) partial += ".rank" + std::to_string(r.rank);
-            unlink((partial + ".csv").c_str());
+            unlink((partial + extension(c.file_type)).c_str());
         }
     }
     if (c.save_wavefns) save_wavefunction(r, wnum, converged);                                           // grid.rs:223-237
@@ -285,6 +277,36 @@ int main(int argc, char** argv) {
         else if (a == "-s" || a == "--script") script = next();
         else if (a == "-d" || a == "-dd" || a == "-ddd") verbosity += (int)a.size() - 1;
         else if (a == "--check-config") check_only = true;
+        else if (a == "--selftest-trilerp") {
+            // the reference's `interpolation` unit test input (input.rs:733-748): 2x2x2 [1..8] -> 4x4x4
+            Array3 v, out;
+            v.nx = v.ny = v.nz = 2;
+            v.data = {1, 2, 3, 4, 5, 6, 7, 8};
+            out.nx = out.ny = out.nz = 4;
+            out.data.assign(64, 0.0);
+            trilerp_resize(v, out);
+            for (double d : out.data) printf("%.17g\n", d);
+            return 0;
+        } else if (a == "--selftest-formats") {
+            // write a deterministic 3x4x5 array in every supported format under the given directory, read it back
+            const std::string dir = next();
+            Array3 v;
+            v.nx = 3; v.ny = 4; v.nz = 5;
+            for (int i = 0; i < 60; ++i) v.data.push_back(std::sin(0.37 * i) * std::pow(10.0, (i % 7) - 3));
+            for (int ft = 0; ft < 3; ++ft) {
+                write_array(dir + "/array", ft, v);
+                Array3 back;
+                if (!read_array(dir + "/array", ft, back) || back.nx != 3 || back.ny != 4 || back.nz != 5 || back.data != v.data) {
+                    fprintf(stderr, "format %d round trip failed\n", ft);
+                    return 1;
+                }
+            }
+            std::vector<double> padded(5 * 6 * 7);
+            embed_work(v, padded, 3, 4, 5, 1);
+            if (extract_work(padded.data(), 3, 4, 5, 1).data != v.data) return 1;
+            puts("formats ok");
+            return 0;
+        }
         else if (a == "--no-output") no_output = true;
         else if (a == "--output-root") outroot = next();
         else if (a == "--rendezvous-file") rdv = next();
@@ -337,7 +359,7 @@ int main(int argc, char** argv) {
         // potential::load_arrays (potential.rs:75-175)
         if (c.potential == 12) {  // FromFile
             std::vector<double> v(d.padded());
-            if (!read_csv_work("input/potential.csv", v, d)) throw std::runtime_error("LoadPotential: input/potential.csv not found");
+            if (!read_work("input/potential", c.file_type, v, d)) throw std::runtime_error("LoadPotential: input/potential.{mpk,csv,json} not found");
             r.ck(wafer_set_potential(r.ctx, v.data()), "wafer_set_potential");
         } else if (c.potential == 13) {  // FromScript
             std::vector<double> v(d.padded());
@@ -356,21 +378,21 @@ int main(int argc, char** argv) {
         if (c.save_potential && !r.outdir.empty() && r.rank == 0) {  // potential.rs:163-172
             std::vector<double> v(d.padded());
             r.ck(wafer_get_potential(r.ctx, v.data()), "wafer_get_potential");
-            if (r.world == 1) write_csv_work(r.outdir + "/potential.csv", v.data(), d);
+            if (r.world == 1) write_work(r.outdir + "/potential", c.file_type, v.data(), d);
         }
 
         // run (grid.rs:31-47): lower states from ./input when starting above the ground state
         for (unsigned w = 0; w < c.wavenum; ++w) {  // input::load_wavefunctions (input.rs:487-505)
             std::vector<double> q(d.padded());
-            if (!read_csv_work("input/wavefunction_" + std::to_string(w) + ".csv", q, d))
-                throw std::runtime_error("LoadWavefunction: input/wavefunction_" + std::to_string(w) + ".csv is required when wavenum > 0");
+            if (!read_work("input/wavefunction_" + std::to_string(w), c.file_type, q, d))
+                throw std::runtime_error("LoadWavefunction: input/wavefunction_" + std::to_string(w) + ".{mpk,csv,json} is required when wavenum > 0");
             r.ck(wafer_push_lower(r.ctx, q.data()), "wafer_push_lower");
         }
         // config::set_initial_conditions (config.rs:577-627)
         if (c.wavenum == 0) {
             if (c.init_condition == 0) {
                 std::vector<double> phi(d.padded());
-                if (!read_csv_work("input/wavefunction_0.csv", phi, d)) throw std::runtime_error("LoadWavefunction: input/wavefunction_0.csv not found");
+                if (!read_work("input/wavefunction_0", c.file_type, phi, d)) throw std::runtime_error("LoadWavefunction: input/wavefunction_0.{mpk,csv,json} not found");
                 r.ck(wafer_set_phi(r.ctx, phi.data()), "wafer_set_phi");
             } else if (c.init_condition == 1) {  // Gaussian (config.rs:636-642): thread_rng there, so any seed is as good
                 std::vector<double> phi(d.padded(), 0.0);
