@@ -7,7 +7,7 @@
 
 Workload (BASELINE.json configs[3]): 1024^3, ThreePoint, gen_potential.py's Poschl-Teller potential, Boolean
 initial condition, ground state; x-slab decomposed over N GPUs of one box (strong scaling).  One "step" is one
-`evolve(wnum=0, screen_update)` call = SWEEPS lattice sweeps (grid.rs:544-687).  `value` counts
+`evolve(wnum=0, screen_update)` call = SWEEPS lattice sweeps (grid.rs:544-687; default 1000 = wafer.yaml:98).  `value` counts
 nx*ny*nz*SWEEPS*K updates over the max-over-ranks device time; `e2e` adds, every step, the host->device copy of
 psi from pinned memory before evolve and the device->host copy of the evolved psi after it (what a stateless
 drop-in of `evolve(&mut Array3)` has to do).  Prints ONE JSON line on rank 0.
@@ -33,7 +33,8 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--grid", type=int, default=1024, help="lattice edge N (N^3 work sites)")
-    ap.add_argument("--sweeps", type=int, default=400, help="lattice sweeps per step (= output.screen_update)")
+    ap.add_argument("--sweeps", type=int, default=1000,
+                    help="lattice sweeps per step = output.screen_update; 1000 is the reference's default (wafer.yaml:98)")
     ap.add_argument("--stencil", default="ThreePoint", choices=["ThreePoint", "FivePoint", "SevenPoint"])
     ap.add_argument("--flags", type=int, default=0, help="wafer_params.flags (1 = A/B arrays, 4 = simple sweep)")
     ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: NCCL send/recv halos instead of fused peer stores")
