@@ -33,6 +33,8 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--grid", type=int, default=1024, help="lattice edge N (N^3 work sites)")
+    ap.add_argument("--nx", type=int, default=0,
+                    help="x extent (the decomposed axis) if not N: e.g. --grid 2048 --nx 256 is one GPU's share of C5")
     ap.add_argument("--sweeps", type=int, default=1000,
                     help="lattice sweeps per step = output.screen_update; 1000 is the reference's default (wafer.yaml:98)")
     ap.add_argument("--stencil", default="ThreePoint", choices=["ThreePoint", "FivePoint", "SevenPoint"])
@@ -145,12 +147,13 @@ def reference_main(args):
 
 def workload_config(args, world):
     n = args.grid
-    return {"workload": "C4: %d^3 %s, Poschl-Teller (gen_potential.py formula, lam=6), Boolean IC, ground state; "
-                        "step = evolve(wnum=0, screen_update=%d)" % (n, args.stencil, args.sweeps),
-            "grid": [n, n, n], "stencil": args.stencil, "sweeps_per_step": args.sweeps,
+    nx = args.nx or n
+    return {"workload": "C4: %dx%dx%d %s, Poschl-Teller (gen_potential.py formula, lam=6), Boolean IC, ground state; "
+                        "step = evolve(wnum=0, screen_update=%d)" % (nx, n, n, args.stencil, args.sweeps),
+            "grid": [nx, n, n], "stencil": args.stencil, "sweeps_per_step": args.sweeps,
             "decomposition": ("x-slab x%d, halo: %s" % (world, "NCCL send/recv" if args.no_p2p else "fused peer stores (CUDA IPC over NVLink)"))
             if world > 1 else "single GPU",
-            "l2": "inputs larger than L2 (%.1f GB per field per GPU vs 126 MB)" % (n ** 3 * 8 / world / 1e9)}
+            "l2": "inputs larger than L2 (%.1f GB per field per GPU vs 126 MB)" % (nx * n * n * 8 / world / 1e9)}
 
 
 # ------------------------------------------------------------------------------------------------- B200 arm
@@ -177,8 +180,12 @@ def measure(lat, args, n, world, dist, steps, warmup, sampler=None):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.barrier()
         ms = float(t.item())
-    glups = n ** 3 * args.sweeps * steps / (ms * 1e-3) / 1e9
+    glups = sites(args, n) * args.sweeps * steps / (ms * 1e-3) / 1e9
     return glups, ms, launches, clocks
+
+
+def sites(args, n):
+    return (args.nx or n) * n * n if n == args.grid else n ** 3
 
 
 def hbm_peak():
@@ -228,7 +235,8 @@ def b200_main(args):
 
     n = args.grid
     dn, dt, mass = physical_params(n)
-    lat = wafer_b200.Lattice((n, n, n), args.stencil, dn=dn, dt=dt, mass=mass, device=local_rank, rank=rank, world=world,
+    nsites = sites(args, n)
+    lat = wafer_b200.Lattice((args.nx or n, n, n), args.stencil, dn=dn, dt=dt, mass=mass, device=local_rank, rank=rank, world=world,
                              nccl_id=nccl_id, flags=args.flags)
     if world > 1 and not args.no_p2p:
         # fused halo: boundary CTAs store into the neighbours' ghost planes through CUDA-IPC mapped peer memory
@@ -253,7 +261,7 @@ def b200_main(args):
     steps_per_launch = 2 if lat.sweep_variant.startswith("tb2") else 1
     n_main = sweeps_total // steps_per_launch + sweeps_total % steps_per_launch
     launch_ms = ms / n_main
-    updates_per_launch = n ** 3 / world * sweeps_total / n_main
+    updates_per_launch = nsites / world * sweeps_total / n_main
     achieved = BYTES_PER_UPDATE * updates_per_launch / (launch_ms * 1e-3) / 1e9
     traffic, traffic_note = ncu_traffic(lat.sweep_variant, updates_per_launch)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -300,7 +308,7 @@ def b200_main(args):
                 tot += ms_e
             # feed the evolved state back in (keeps the ring zero and the values finite)
             h_in[q0 - p0:q0 - p0 + (q1 - q0)] = h_out
-        e2e = {"value": n ** 3 * args.sweeps * e_steps / (tot * 1e-3) / 1e9, "unit": "GLUPS",
+        e2e = {"value": nsites * args.sweeps * e_steps / (tot * 1e-3) / 1e9, "unit": "GLUPS",
                "h2d_bytes_per_step": int(h_in.size * 8 * world), "d2h_bytes_per_step": int(h_out.size * 8 * world),
                "steps": e_steps, "ms_per_step": tot / e_steps,
                "call": "wafer_set_phi_slab(pinned) -> wafer_evolve(0, %d) -> wafer_get_phi_slab(pinned)" % args.sweeps}
@@ -311,7 +319,7 @@ def b200_main(args):
     lat.close()
 
     extra = {}
-    if rank == 0 and world == 1 and not args.no_512 and n != 512:
+    if rank == 0 and world == 1 and not args.no_512 and n != 512 and not args.nx:
         # BASELINE metric's other quoted point: 512^3 on one GPU
         a2 = argparse.Namespace(**vars(args))
         a2.grid = 512
