@@ -88,13 +88,13 @@ def test_default_run_matches_oracle(binary, oracle, tmp_path):
     assert obs["binding_energy"] == pytest.approx(rec[-1]["E"], rel=1e-9)  # Harmonic: pot_sub = 0
     assert obs["r"] == pytest.approx(np.sqrt(rec[-1]["r2"] / rec[-1]["norm2"]), rel=1e-9)
     assert obs["l_r"] == pytest.approx(50 / obs["r"], rel=1e-12)
-    wf = np.loadtxt(outdir / "wavefunction_0.csv", delimiter=",")
-    assert wf.shape == (125000, 4)
-    got = wf[:, 3].reshape(50, 50, 50)
+    wf = json.loads((outdir / "wavefunction_0.json").read_text())  # file_type: Json -> ndarray serde record
+    assert wf["v"] == 1 and wf["dim"] == [50, 50, 50]
+    got = np.array(wf["data"]).reshape(50, 50, 50)
     ref_work = phi[1:-1, 1:-1, 1:-1]
     assert np.linalg.norm(got - ref_work) / np.linalg.norm(ref_work) < 1e-8
     # first excited state: the driver seeds it deterministically (generators.cuh seed_poly), so it is comparable
-    assert (outdir / "observables_1.json").exists() and (outdir / "wavefunction_1.csv").exists()
+    assert (outdir / "observables_1.json").exists() and (outdir / "wavefunction_1.json").exists()
     lowers = [phi]
     p1 = oracle.seed_from_state(g, phi)
     conv1, rec1 = oracle.solve(g, v, a, b, p1, lowers=lowers, tolerance=1e-4, screen_update=1000, max_records=400)
@@ -102,7 +102,7 @@ def test_default_run_matches_oracle(binary, oracle, tmp_path):
     e1 = json.loads((outdir / "observables_1.json").read_text())["energy"]
     assert e1 == pytest.approx(rec1[-1]["E"], rel=1e-9) and e1 > obs["energy"]
     assert len(rows) == 19 + len(rec1)
-    wf1 = np.loadtxt(outdir / "wavefunction_1.csv", delimiter=",")[:, 3].reshape(50, 50, 50)
+    wf1 = np.array(json.loads((outdir / "wavefunction_1.json").read_text())["data"]).reshape(50, 50, 50)
     assert np.linalg.norm(wf1 - p1[1:-1, 1:-1, 1:-1]) / np.linalg.norm(p1[1:-1, 1:-1, 1:-1]) < 1e-8
 
 
