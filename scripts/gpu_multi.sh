@@ -7,7 +7,7 @@ OUT=gpurun_out/$LABEL
 mkdir -p "$OUT"
 nvidia-smi --query-gpu=index,name,clocks.sm,clocks.max.sm,power.draw --format=csv > "$OUT/gpu.csv" 2>&1
 nvidia-smi topo -m > "$OUT/topo.txt" 2>&1
-for mode in 1 0; do
+for mode in ${CHECK_MODES:-1 0}; do
   WAFER_P2P=$mode timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29601+mode)) \
       scripts/multigpu_check.py > "$OUT/multigpu_check_p2p$mode.log" 2>&1
   echo "multigpu_check p2p=$mode rc=$?" | tee -a "$OUT/rc.log"; grep '^{' "$OUT/multigpu_check_p2p$mode.log" | tail -1; tail -2 "$OUT/multigpu_check_p2p$mode.log" | cut -c1-300
