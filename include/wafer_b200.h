@@ -45,8 +45,7 @@ typedef enum {
 
 /* flags */
 #define WAFER_FLAG_AB_ARRAYS 0x1u   /* keep A and B as arrays (32 B/update) instead of recomputing them from V in the sweep */
-#define WAFER_FLAG_NO_GRAPH  0x2u   /* never capture sweeps into CUDA graphs                                               */
-#define WAFER_FLAG_SIMPLE_SWEEP 0x4u /* force the plain register-queue sweep (no shared-memory/TMA pipeline, no time tiling) */
+#define WAFER_FLAG_SIMPLE_SWEEP 0x4u /* force the plain register-queue sweep (no TMA pipeline, one step per pass)          */
 
 typedef struct {
     uint64_t nx, ny, nz;   /* WORK sizes = config.grid.size.{x,y,z}            (config.rs:16-23)           */
@@ -55,7 +54,7 @@ typedef struct {
     int32_t device;        /* CUDA device ordinal used by this process; -1 = LOCAL_RANK env or 0           */
     uint32_t rank, world;  /* slab decomposition; world = 0 or 1 means single GPU                          */
     const uint8_t *nccl_id;/* 128-byte ncclUniqueId made by wafer_nccl_unique_id on rank 0; NULL if world<=1 */
-    uint32_t max_lower;    /* wavemax: how many converged lower states may be stored (config.rs:312)        */
+    uint32_t max_lower;    /* wavemax (config.rs:312); advisory — lower states are allocated as they are pushed */
     uint32_t flags;
 } wafer_params;
 

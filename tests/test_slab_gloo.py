@@ -89,6 +89,109 @@ def _worker(rank, world, port, ext, shape, steps, nlow, out_dir):
     dist.destroy_process_group()
 
 
+def _exchange_depth(dist, torch, loc, gx, rank, world):
+    """depth-gx ghost swap (the ThreePoint slabs keep gx = 2 ghost planes for the two-steps-per-pass sweep)"""
+    reqs, bufs = [], []
+    L = loc.shape[0] - 2 * gx
+    if rank > 0:
+        s = torch.from_numpy(np.ascontiguousarray(loc[gx:2 * gx]))
+        r = torch.empty_like(s)
+        reqs += [dist.isend(s, rank - 1), dist.irecv(r, rank - 1)]
+        bufs.append((slice(0, gx), r))
+    if rank < world - 1:
+        s = torch.from_numpy(np.ascontiguousarray(loc[L:L + gx]))
+        r = torch.empty_like(s)
+        reqs += [dist.isend(s, rank + 1), dist.irecv(r, rank + 1)]
+        bufs.append((slice(L + gx, L + 2 * gx), r))
+    for q in reqs:
+        q.wait()
+    for sl, r in bufs:
+        loc[sl] = r.numpy()
+
+
+def _worker_two_step(rank, world, port, shape, passes, tail, out_dir):
+    """Protocol of the time-tiled path (wafer_b200.cu::wafer_evolve, `two` passes): ghost depth 2, TWO sweeps per halo
+    exchange — the first sweep is also evaluated on the inner ghost plane (redundantly, from the depth-2 ghosts), the
+    second on the owned planes only; planes outside the global lattice stay exactly zero."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+
+    import np_restatement as npr
+    import wafer_b200
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    e, gx, (nx, ny, nz) = 1, 2, shape
+    dn, dt, mass = 0.1, 2e-3, 1.0
+    rng = np.random.default_rng(9)
+    P = (nx + 2, ny + 2, nz + 2)
+    v = rng.normal(size=P)
+    phi = np.zeros(P)
+    npr.work(phi, e)[...] = rng.normal(size=shape)
+    a, b = npr.build_ab(v, dt)
+    x0, x1 = wafer_b200.slab_partition(nx, world, rank)
+    L = x1 - x0
+
+    def slab(arr):  # local planes [-gx, L+gx) = padded planes [x0+1-gx, x1+1+gx), zero outside the array
+        out = np.zeros((L + 2 * gx,) + P[1:])
+        lo, hi = x0 + 1 - gx, x1 + 1 + gx
+        clo, chi = max(lo, 0), min(hi, P[0])
+        out[clo - lo:chi - lo] = arr[clo:chi]
+        return out
+
+    loc, la, lb = slab(phi), slab(a), slab(b)
+    inside = np.array([0 <= x0 + i - gx < nx for i in range(L + 2 * gx)])  # local plane inside the global lattice
+
+    def sweep_planes(src, lo, hi):
+        """one step on local planes [lo, hi) (indices into the slab array), others copied"""
+        new = npr.sweep(src, la, lb, e, dn, dt, mass)  # updates planes [1, n-1)
+        out = src.copy()
+        out[lo:hi] = new[lo:hi]
+        out[~inside] = 0.0  # the ring never changes
+        return out
+
+    for _ in range(passes):
+        lvl1 = sweep_planes(loc, gx - 1, gx + L + 1)   # first step incl. one ghost plane each side
+        loc = sweep_planes(lvl1, gx, gx + L)           # second step on owned planes
+        _exchange_depth(dist, torch, loc, gx, rank, world)
+    for _ in range(tail):                              # odd tail: one step, still a depth-2 exchange
+        loc = sweep_planes(loc, gx, gx + L)
+        _exchange_depth(dist, torch, loc, gx, rank, world)
+    np.save(os.path.join(out_dir, "slab2_%d.npy" % rank), loc)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,shape,passes,tail", [(2, (10, 6, 7), 3, 1), (3, (13, 5, 6), 2, 0), (2, (9, 4, 5), 2, 2)])
+def test_two_steps_per_exchange_protocol(tmp_path, world, shape, passes, tail):
+    import torch.multiprocessing as mp
+
+    import np_restatement as npr
+    import wafer_b200
+
+    port = 31500 + (os.getpid() + 11 * world + passes) % 2000
+    mp.spawn(_worker_two_step, args=(world, port, shape, passes, tail, str(tmp_path)), nprocs=world, join=True)
+    nx, ny, nz = shape
+    rng = np.random.default_rng(9)
+    P = (nx + 2, ny + 2, nz + 2)
+    v = rng.normal(size=P)
+    phi = np.zeros(P)
+    npr.work(phi, 1)[...] = rng.normal(size=shape)
+    a, b = npr.build_ab(v, 2e-3)
+    for _ in range(2 * passes + tail):
+        phi = npr.sweep(phi, a, b, 1, 0.1, 2e-3, 1.0)
+    for r in range(world):
+        x0, x1 = wafer_b200.slab_partition(nx, world, r)
+        loc = np.load(tmp_path / ("slab2_%d.npy" % r))
+        assert np.array_equal(loc[2:2 + x1 - x0], phi[x0 + 1:x1 + 1])          # owned planes: bit-identical
+        for gpl, row in ((x0 - 1, loc[0]), (x0, loc[1]), (x1 + 1, loc[-2]), (x1 + 2, loc[-1])):  # depth-2 ghosts
+            expect = phi[gpl] if 0 <= gpl < P[0] else np.zeros(P[1:])
+            assert np.array_equal(row, expect)
+
+
 @pytest.mark.parametrize("world,ext,shape,nlow", [(2, 1, (10, 6, 7), 0), (2, 2, (9, 6, 8), 0), (3, 3, (11, 8, 8), 0),
                                                    (2, 1, (8, 6, 6), 2)])
 def test_slab_decomposition_matches_single_domain(tmp_path, world, ext, shape, nlow):

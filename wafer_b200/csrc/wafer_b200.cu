@@ -36,7 +36,6 @@ struct wafer_ctx {
     bool onfly = true;
     bool use_tb = false;            // time-tiled TMA sweep available (ThreePoint, V on the fly)
     CUtensorMap tm_psi[2], tm_v;    // TMA descriptors of the interior of psi[0], psi[1], v
-    int tb_xchunk = 64;
     int den_ok = 0;
     cudaStream_t s_main = nullptr, s_halo = nullptr;
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_main = nullptr, ev_halo = nullptr;
@@ -204,11 +203,6 @@ int init_tb(wafer_ctx* ctx) {
     CK(cudaFuncSetAttribute(tb::sweep_tb2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb::SMEM_BYTES));
     const double den = denominator(ctx);
     ctx->den_ok = (den > 7.888609052210118e-31 && den < 1.2676506002282294e30) ? 1 : 0;  // 2^-100 .. 2^100
-    // x chunk: enough CTAs for ~8 waves, at most 128 planes (pipeline fill is 4 planes per chunk)
-    const long long tiles = (long long)ceil_div(ctx->g.nz, tb::TZ) * ceil_div(ctx->g.ny, tb::TY);
-    int chunk = 128;
-    while (chunk > 16 && tiles * ceil_div(ctx->g.L, chunk) < (long long)ctx->sm_count * 6) chunk /= 2;
-    ctx->tb_xchunk = chunk;
     ctx->use_tb = true;
     return WAFER_OK;
 }
