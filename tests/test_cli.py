@@ -141,3 +141,42 @@ def test_array_formats_roundtrip_and_serde_layout(binary, tmp_path):
     assert rows.shape == (60, 4) and list(rows[:, 3]) == rec[2]
     assert [tuple(int(v) for v in row[:3]) for row in rows[:6]] == [(0, 0, 0), (0, 0, 1), (0, 0, 2), (0, 0, 3), (0, 0, 4),
                                                                    (0, 1, 0)]
+
+
+@pytest.mark.gpu
+def test_script_potential_and_input_files(binary, tmp_path):
+    """FromScript goes through the reference's stdin/stdout protocol (input.rs:186-248) and must give the same run as the
+    built-in Harmonic potential; a coarse wavefunction in ./input is up-sampled (input.rs:149-176) and used as the start."""
+    import shutil
+    base = open(DEFAULT).read().replace("x: 50", "x: 20").replace("y: 50", "y: 20").replace("z: 50", "z: 20")
+    base = base.replace("dn: 0.01", "dn: 0.25").replace("dt: 3e-5", "dt: 0.01").replace("mass: 15.9994", "mass: 1.0")
+    base = base.replace("wavemax: 1", "wavemax: 0").replace("tolerance: 1e-4", "tolerance: 1e-9")
+    base = base.replace("screen_update: 1000", "screen_update: 100").replace("file_type: Json", "file_type: Messagepack")
+    (tmp_path / "harm.yaml").write_text(base)
+    (tmp_path / "script.yaml").write_text(base.replace("potential: Harmonic", "potential: FromScript"))
+    shutil.copy(os.path.join(ROOT, "tests", "golden", "script_potential.py"), tmp_path / "gen.py")
+    energies = []
+    for cfg, extra in (("harm.yaml", []), ("script.yaml", ["-s", "gen.py"])):
+        r = subprocess.run([binary, "-c", cfg, "--output-root", cfg + ".out"] + extra, capture_output=True, text=True,
+                           cwd=tmp_path, timeout=300)
+        assert r.returncode == 0, r.stderr[-1500:]
+        outdir = next((tmp_path / (cfg + ".out")).iterdir())
+        import msgpack
+        state, energy, binding, rr, l_r = msgpack.unpackb((outdir / "observables_0.mpk").read_bytes())
+        assert state == 0 and binding == energy
+        energies.append(energy)
+        rec = msgpack.unpackb((outdir / "wavefunction_0.mpk").read_bytes())
+        assert rec[0] == 1 and rec[1] == [20, 20, 20]
+    assert energies[0] == energies[1]  # identical potentials bit for bit -> identical runs
+    # coarse-to-fine restart: the converged 20^3 state as ./input/wavefunction_0.mpk for a 40^3 run
+    (tmp_path / "input").mkdir()
+    shutil.copy(next((tmp_path / "harm.yaml.out").iterdir()) / "wavefunction_0.mpk", tmp_path / "input" / "wavefunction_0.mpk")
+    fine = base.replace("x: 20", "x: 40").replace("y: 20", "y: 40").replace("z: 20", "z: 40").replace("dn: 0.25", "dn: 0.125")
+    fine = fine.replace("dt: 0.01", "dt: 0.0025").replace("init_condition: Boolean", "init_condition: FromFile")
+    (tmp_path / "fine.yaml").write_text(fine)
+    r = subprocess.run([binary, "-c", "fine.yaml", "--output-root", "fine.out"], capture_output=True, text=True, cwd=tmp_path,
+                       timeout=300)
+    assert r.returncode == 0, r.stderr[-1500:]
+    rows = [l for l in r.stdout.splitlines() if re.match(r"\s+│\s+[0-9.]+ │", l)]
+    e_start = float(rows[0].split("│")[2])
+    assert abs(e_start - energies[0]) < 0.02  # the up-sampled coarse solution is already close to the fine one
