@@ -353,6 +353,10 @@ def test_default_wafer_yaml_ground_state(wb, oracle):
         assert lat.num_lowers == 1 and np.array_equal(lat.get_lower(0), got)
     assert conv and conv_ref and len(rec) == len(rec_ref) == 19
     assert rec[-1]["step"] == 18000 and abs(rec[-1]["E"] - 3.56925) < 1e-4
+    import json, os
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "c1_default_records.json")))
+    for r, gr in zip(rec, gold["state0"]["records"]):  # stored fixture (tests/golden/make_golden.py)
+        assert r["step"] == gr["step"] and abs(r["E"] - gr["E"]) <= E_TOL * abs(gr["E"])
     for r, rr in zip(rec, rec_ref):
         assert r["step"] == rr["step"] and r["tau"] == rr["tau"]
         assert abs(r["E"] - rr["E"]) <= E_TOL * abs(rr["E"])

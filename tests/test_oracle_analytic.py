@@ -118,3 +118,24 @@ def test_sweep_is_linear(oracle):
     for arr in (x, y, z):
         oracle.evolve(g, arr, a, b, 3)
     assert np.allclose(z, 2.0 * x - 0.5 * y, rtol=0, atol=1e-13)
+
+
+def test_default_config_golden_records(oracle):
+    """tests/golden/c1_default_records.json (made by tests/golden/make_golden.py): BASELINE config C1 ground state."""
+    import hashlib
+    import json
+    import os
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "c1_default_records.json")))
+    g = oracle.make_grid(50, 50, 50, ext=1, dn=0.01, dt=3e-5, mass=15.9994)
+    v = oracle.potential(g, "Harmonic")
+    a, b = oracle.build_ab(v, g.dt)
+    phi = oracle.initial_condition(g, "Boolean")
+    conv, rec = oracle.solve(g, v, a, b, phi, tolerance=1e-4, screen_update=1000)
+    assert conv and len(rec) == len(gold["state0"]["records"]) == 19
+    for r, gr in zip(rec, gold["state0"]["records"]):
+        assert r["step"] == gr["step"] and r["E"] == pytest.approx(gr["E"], rel=1e-13)
+    assert rec[-1]["step"] == 18000 and rec[-1]["E"] == pytest.approx(3.56925, abs=1e-5)     # BASELINE.md §5
+    assert np.sqrt(rec[-1]["r2"] / rec[-1]["norm2"]) == pytest.approx(16.09, abs=5e-3)
+    if oracle.num_threads() == gold.get("threads", oracle.num_threads()):
+        # sums are per-plane, so the state is independent of the thread count: the hash must match
+        assert hashlib.sha256(phi.tobytes()).hexdigest() == gold["state0"]["phi_sha256"]
