@@ -9,8 +9,8 @@ Workload (BASELINE.json configs[3]): 1024^3, ThreePoint, gen_potential.py's Posc
 initial condition, ground state; x-slab decomposed over N GPUs of one box (strong scaling).  One "step" is one
 `evolve(wnum=0, screen_update)` call = SWEEPS lattice sweeps (grid.rs:544-687; default 1000 = wafer.yaml:98).  `value` counts
 nx*ny*nz*SWEEPS*K updates over the max-over-ranks device time; `e2e` adds, every step, the host->device copy of
-psi from pinned memory before evolve and the device->host copy of the evolved psi after it (what a stateless
-drop-in of `evolve(&mut Array3)` has to do).  Prints ONE JSON line on rank 0.
+psi from pinned memory before evolve, one observables check (grid.rs:127-135) and the device->host copy of the evolved
+psi after it (what a stateless drop-in of the reference's loop body has to do).  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -295,6 +295,7 @@ def b200_main(args):
             lat.timer_begin()
             lat.set_phi_slab(h_in)
             lat.evolve(0, args.sweeps)
+            obs = lat.check(0)  # the loop body of grid.rs:126-221: observables + normalise, 4 scalars back to the host
             lat.get_phi_slab(h_out)
             ms_e = lat.timer_end()
             wall = (time.perf_counter() - t0) * 1e3
@@ -311,7 +312,8 @@ def b200_main(args):
         e2e = {"value": nsites * args.sweeps * e_steps / (tot * 1e-3) / 1e9, "unit": "GLUPS",
                "h2d_bytes_per_step": int(h_in.size * 8 * world), "d2h_bytes_per_step": int(h_out.size * 8 * world),
                "steps": e_steps, "ms_per_step": tot / e_steps,
-               "call": "wafer_set_phi_slab(pinned) -> wafer_evolve(0, %d) -> wafer_get_phi_slab(pinned)" % args.sweeps}
+               "call": "wafer_set_phi_slab(pinned) -> wafer_evolve(0, %d) -> wafer_check(0) -> wafer_get_phi_slab(pinned)"
+                       % args.sweeps, "last_energy": obs["energy"] / obs["norm2"]}
         wafer_b200.pinned_free(host)
 
     info = lat.device_info()
