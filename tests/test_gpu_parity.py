@@ -150,6 +150,48 @@ def test_time_tiled_sweep_bitwise(wb, oracle, shape, steps):
     assert np.array_equal(got, phi)
 
 
+@pytest.mark.parametrize("dn,mass", [(1e-18, 1.3), (0.05, -1.3), (1e17, 1.0)])
+def test_time_tiled_sweep_cold_division_path(wb, oracle, dn, mass):
+    """Denominators outside the hoisted-division window (or negative) must take the IEEE cold path and stay bit-exact."""
+    shape = (21, 33, 70)
+    rng = np.random.default_rng(41)
+    dt = 1e-3
+    g = oracle.make_grid(*shape, ext=1, dn=dn, dt=dt, mass=mass)
+    v = rng.normal(size=g.padded_shape)
+    phi = np.zeros(g.padded_shape)
+    npr.work(phi, 1)[...] = rng.normal(size=shape) * 1e-3
+    a, b = oracle.build_ab(v, dt)
+    with wb.Lattice(shape, dn=dn, dt=dt, mass=mass) as lat:
+        lat.set_potential(v)
+        lat.set_phi(phi)
+        lat.evolve(0, 2)
+        got = lat.get_phi()
+    with np.errstate(all="ignore"):
+        oracle.evolve(g, phi, a, b, 2)
+    assert np.array_equal(got, phi, equal_nan=True)
+
+
+def test_time_tiled_sweep_with_zeros_and_denormals(wb, oracle):
+    """Exact zeros (compact support), denormal and huge values leave the fast-division window site by site."""
+    shape = (40, 33, 70)
+    g = oracle.make_grid(*shape, ext=1, dn=0.05, dt=6.25e-4, mass=1.0)
+    v = oracle.potential(g, "Harmonic")
+    a, b = oracle.build_ab(v, g.dt)
+    phi = np.zeros(g.padded_shape)
+    phi[10:20, 8:20, 30:50] = np.random.default_rng(3).normal(size=(10, 12, 20))
+    phi[25:30, 5:9, 3:9] = 1e-310
+    phi[32:36, 20:25, 60:66] = 1e-250
+    phi[5:7, 25:30, 10:14] = 1e290
+    with wb.Lattice(shape, dn=g.dn, dt=g.dt, mass=g.mass) as lat:
+        lat.set_potential(v)
+        lat.set_phi(phi)
+        lat.evolve(0, 6)
+        got = lat.get_phi()
+    oracle.evolve(g, phi, a, b, 6)
+    assert np.array_equal(got, phi)
+    assert np.array_equal(np.signbit(got), np.signbit(phi))  # signed zeros too
+
+
 def test_simple_sweep_flag_bitwise(wb, oracle):
     g, v, phi = _rand_state(oracle, (40, 33, 70), 1, 31)
     a, b = oracle.build_ab(v, g.dt)
