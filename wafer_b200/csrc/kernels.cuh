@@ -143,7 +143,7 @@ __device__ __forceinline__ void block_reduce_store(double (&v)[NS], double* __re
     }
 }
 
-// One CTA sums partials[s][0..nblocks) in a fixed order -> out[s] (+= when accumulate).
+// One CTA sums partials[s][0..nblocks) in a fixed order -> out[s]: run-to-run deterministic, no f64 atomics.
 template <int NS>
 __global__ void __launch_bounds__(1024) finalize_kernel(const double* __restrict__ partials, int nblocks,
                                                         double* __restrict__ out) {

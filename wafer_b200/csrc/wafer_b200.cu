@@ -333,11 +333,22 @@ int observables_device(wafer_ctx* ctx) {
     return finalize(ctx, 4, nb, SL_OBS, ctx->s_main);
 }
 
+// a fused-halo wait that gave up (dead or desynchronised neighbour) must not go unnoticed: every call that hands
+// numbers back to the host checks the device-side timeout flag after its synchronisation
+int check_p2p_timeout(wafer_ctx* ctx) {
+    if (!ctx->p2p_timeout) return WAFER_OK;
+    int t = 0;
+    CK(cudaMemcpyAsync(&t, ctx->p2p_timeout, sizeof(int), cudaMemcpyDeviceToHost, ctx->s_main));
+    CK(cudaStreamSynchronize(ctx->s_main));
+    if (t) { ctx->err = "fused halo: timed out waiting for a neighbour GPU's pass flag"; return WAFER_ERR_NCCL; }
+    return WAFER_OK;
+}
+
 int read_scalars(wafer_ctx* ctx, int slot, int n, double* out) {
     CK(cudaMemcpyAsync(ctx->h_scal + slot, ctx->scal + slot, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->s_main));
     CK(cudaStreamSynchronize(ctx->s_main));
     for (int i = 0; i < n; ++i) out[i] = ctx->h_scal[slot + i];
-    return WAFER_OK;
+    return check_p2p_timeout(ctx);
 }
 
 // ---- host <-> device layout ------------------------------------------------------------------------------
@@ -935,12 +946,7 @@ int wafer_synchronize(wafer_ctx* ctx) {
     CK(cudaSetDevice(ctx->dev));
     CK(cudaStreamSynchronize(ctx->s_halo));
     CK(cudaStreamSynchronize(ctx->s_main));
-    if (ctx->p2p_timeout) {
-        int t = 0;
-        CK(cudaMemcpy(&t, ctx->p2p_timeout, sizeof(int), cudaMemcpyDeviceToHost));
-        if (t) { ctx->err = "fused halo: timed out waiting for a neighbour GPU's pass flag"; return WAFER_ERR_NCCL; }
-    }
-    return WAFER_OK;
+    return check_p2p_timeout(ctx);
 }
 
 int wafer_timer_begin(wafer_ctx* ctx) {
@@ -1011,6 +1017,7 @@ int wafer_p2p_connect(wafer_ctx* ctx, const uint8_t* lower, const uint8_t* upper
     REQUIRE((ctx->rank == 0) == (lower == nullptr) && (ctx->rank == ctx->world - 1) == (upper == nullptr),
             "pass the export blobs of rank-1 and rank+1 (NULL at the ends of the chain)");
     CK(cudaSetDevice(ctx->dev));
+    REQUIRE(!ctx->p2p, "wafer_p2p_connect was already called on this context");
     const uint8_t* blobs[2] = {lower, upper};
     for (int n = 0; n < 2; ++n) {
         if (!blobs[n]) continue;
