@@ -23,8 +23,10 @@ def main():
     n = int(os.environ.get("N", "512"))
     dn = 10.24 / n
     for cd in ("ThreePoint", "FivePoint", "SevenPoint"):
-        for flags, tag in ((0, "default"), (4, "simple"), (1, "ab_arrays")):
+        for flags, tag in ((0, "default"), (4, "simple"), (1, "ab_arrays"), (12 if cd == "ThreePoint" else 8, "tma1")):
             if cd != "ThreePoint" and flags == 4:
+                continue
+            if tag == "tma1" and os.environ.get("NO_TMA1"):
                 continue
             with wafer_b200.Lattice((n,) * 3, cd, dn=dn, dt=0.1 * dn * dn, mass=1.0, flags=flags) as lat:
                 lat.generate_potential("Harmonic")
@@ -36,17 +38,21 @@ def main():
                     out["%s_check_ms_%d" % (cd, n)] = timed(lat, lambda: lat.check(0), 5)
     m = int(os.environ.get("M", "256"))
     dm = 10.24 / m
-    with wafer_b200.Lattice((m,) * 3, "ThreePoint", dn=dm, dt=0.1 * dm * dm, mass=1.0) as lat:
-        lat.generate_potential("Harmonic")
-        lat.set_initial_conditions("Boolean")
-        lat.check(0)
-        for k in (1, 2, 3):
-            lat.push_lower()  # any stored state will do for timing
-            lat.phi_seed_from_lower(0)
-            lat.check(k)
-            ms = timed(lat, lambda: lat.evolve(k, 10), 5)
-            out["excited_k%d_glups_%d" % (k, m)] = m ** 3 * 10 / ms / 1e6
-            out["excited_k%d_GBps_algorithmic_%d" % (k, m)] = (48 + 16 * k) * m ** 3 * 10 / ms / 1e6
+    for flags, tag in ((0, ""), (8, "_tma1")):
+        if flags and os.environ.get("NO_TMA1"):
+            continue
+        with wafer_b200.Lattice((m,) * 3, "ThreePoint", dn=dm, dt=0.1 * dm * dm, mass=1.0, flags=flags) as lat:
+            lat.generate_potential("Harmonic")
+            lat.set_initial_conditions("Boolean")
+            lat.check(0)
+            for k in (1, 2, 3):
+                lat.push_lower()  # any stored state will do for timing
+                lat.phi_seed_from_lower(0)
+                lat.check(k)
+                ms = timed(lat, lambda: lat.evolve(k, 10), 5)
+                out["excited_k%d%s_glups_%d" % (k, tag, m)] = m ** 3 * 10 / ms / 1e6
+                if not flags:
+                    out["excited_k%d_GBps_algorithmic_%d" % (k, m)] = (48 + 16 * k) * m ** 3 * 10 / ms / 1e6
     print(json.dumps(out, indent=1))
 
 

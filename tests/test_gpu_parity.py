@@ -192,6 +192,59 @@ def test_time_tiled_sweep_with_zeros_and_denormals(wb, oracle):
     assert np.array_equal(np.signbit(got), np.signbit(phi))  # signed zeros too
 
 
+@pytest.mark.parametrize("ext", [1, 2, 3])
+@pytest.mark.parametrize("shape,steps", [((12, 9, 10), 3), ((50, 37, 21), 4), ((33, 64, 130), 2), ((70, 61, 121), 5),
+                                         ((7, 3, 2), 3), ((131, 31, 59), 2)])
+def test_tma_one_step_sweep_bitwise(wb, oracle, ext, shape, steps):
+    """WAFER_FLAG_TMA_ONE_STEP (8), with the time-tiled kernel switched off (4): every step goes through sweep_tma1."""
+    g, v, phi = _rand_state(oracle, shape, ext, 51 + ext)
+    a, b = oracle.build_ab(v, g.dt)
+    with wb.Lattice(shape, CD[ext], dn=g.dn, dt=g.dt, mass=g.mass, flags=8 | 4) as lat:
+        assert lat.sweep_variant.startswith("tma1")
+        lat.set_potential(v)
+        lat.set_phi(phi)
+        lat.evolve(0, steps)
+        got = lat.get_phi()
+    oracle.evolve(g, phi, a, b, steps)
+    assert np.array_equal(got, phi)
+
+
+@pytest.mark.parametrize("ext,nlow", [(1, 2), (2, 1), (3, 1)])
+def test_tma_one_step_excited_and_mixed(wb, oracle, ext, nlow):
+    """flag 8 alone: ThreePoint ground state = time-tiled pairs + TMA one-step tail; excited steps use the fused norm."""
+    rng = np.random.default_rng(61 + ext)
+    shape = (37, 40, 66)
+    g = oracle.make_grid(*shape, ext=ext, dn=0.1, dt=2e-3, mass=1.0)
+    v = oracle.potential(g, "Harmonic")
+    a, b = oracle.build_ab(v, g.dt)
+    lowers = []
+    for _ in range(nlow):
+        q = np.zeros(g.padded_shape)
+        npr.work(q, ext)[...] = rng.normal(size=shape)
+        q = npr.orthogonalise(q, lowers)
+        lowers.append(np.ascontiguousarray(q / np.sqrt((q * q).sum())))
+    phi = np.zeros(g.padded_shape)
+    npr.work(phi, ext)[...] = rng.normal(size=shape)
+    ref = phi.copy()
+    oracle.set_sum_mode(1)
+    try:
+        with wb.Lattice(shape, CD[ext], dn=g.dn, dt=g.dt, mass=g.mass, flags=8) as lat:
+            lat.set_potential(v)
+            lat.set_phi(phi)
+            lat.evolve(0, 5)
+            ground = lat.get_phi()
+            for q in lowers:
+                lat.push_lower(q)
+            lat.evolve(nlow, 4)
+            got = lat.get_phi()
+        oracle.evolve(g, ref, a, b, 5)
+        assert np.array_equal(ground, ref)
+        oracle.evolve(g, ref, a, b, 4, lowers=lowers)
+    finally:
+        oracle.set_sum_mode(0)
+    assert _l2(got, ref) < 1e-12
+
+
 def test_simple_sweep_flag_bitwise(wb, oracle):
     g, v, phi = _rand_state(oracle, (40, 33, 70), 1, 31)
     a, b = oracle.build_ab(v, g.dt)

@@ -25,6 +25,7 @@ INITIAL_CONDITIONS = {"FromFile": 0, "Gaussian": 1, "Coulomb": 2, "Constant": 3,
 EXT = {"ThreePoint": 1, "FivePoint": 2, "SevenPoint": 3}
 FLAG_AB_ARRAYS = 0x1
 FLAG_SIMPLE_SWEEP = 0x4
+FLAG_TMA_ONE_STEP = 0x8
 
 _STATUS = {1: "INVALID", 2: "NO_DEVICE", 3: "CUDA", 4: "NCCL", 5: "RING_NONZERO", 6: "NOT_READY", 7: "MAX_STEP",
            8: "NONFINITE"}

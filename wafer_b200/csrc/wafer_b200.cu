@@ -18,6 +18,7 @@
 #include "kernels.cuh"
 #include "nccl_dyn.h"
 #include "sweep_tb.cuh"
+#include "sweep_tma1.cuh"
 
 using namespace wafer;
 
@@ -37,6 +38,8 @@ struct wafer_ctx {
     bool use_tb = false;            // time-tiled TMA sweep available (ThreePoint, V on the fly)
     CUtensorMap tm_psi[2], tm_v;    // TMA descriptors of the interior of psi[0], psi[1], v
     int den_ok = 0;
+    bool use_t1 = false;            // TMA-pipelined one-step sweep (WAFER_FLAG_TMA_ONE_STEP)
+    CUtensorMap t1_psi[2], t1_v;
     cudaStream_t s_main = nullptr, s_halo = nullptr;
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_main = nullptr, ev_halo = nullptr;
     double* psi[2] = {nullptr, nullptr};
@@ -151,13 +154,23 @@ int launch_sweep_simple(wafer_ctx* ctx, const double* cur, double* nxt, int xb, 
     return post_launch(ctx);
 }
 
-int sweep_blocks(const wafer_ctx* ctx, int xb, int xe) {
+int simple_blocks(const wafer_ctx* ctx, int xb, int xe) {
     const Geom& g = ctx->g;
     return ceil_div(g.nz, 2 * SW_BX) * ceil_div(g.ny, SW_BY) * ceil_div(xe - xb, SW_XCH);
 }
 
+// forward declarations of the TMA one-step path (defined below, next to the tensor-map helpers)
+template <int E> int launch_sweep_t1(wafer_ctx* ctx, int src, int xb, int xe, bool norm, cudaStream_t st);
+template <int E> int t1_blocks(const wafer_ctx* ctx, int xb, int xe);
+
+// number of per-CTA partial sums the fused-norm sweep over [xb, xe) leaves in ctx->partials
+int sweep_blocks(const wafer_ctx* ctx, int xb, int xe);
+
 int launch_sweep(wafer_ctx* ctx, const double* cur, double* nxt, int xb, int xe, bool norm, long long part_off,
-                 cudaStream_t st) {
+                 cudaStream_t st);
+
+int launch_sweep_plain(wafer_ctx* ctx, const double* cur, double* nxt, int xb, int xe, bool norm, long long part_off,
+                       cudaStream_t st) {
     switch (ctx->p.ext) {
         case 1: return launch_sweep_simple<1>(ctx, cur, nxt, xb, xe, norm, part_off, st);
         case 2: return launch_sweep_simple<2>(ctx, cur, nxt, xb, xe, norm, part_off, st);
@@ -170,7 +183,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int make_tensor_map(wafer_ctx* ctx, CUtensorMap* tm, double* field, int box_rows) {
+int make_tensor_map(wafer_ctx* ctx, CUtensorMap* tm, double* field, int box_rows) {  // 64-column boxes
     static EncodeTiledFn encode = nullptr;
     if (!encode) {
         void* fn = nullptr;
@@ -235,6 +248,84 @@ int launch_sweep_tb2(wafer_ctx* ctx, int src, int xb, int xe, cudaStream_t st, d
                                                                                ctx->p.dt, denominator(ctx), ctx->den_ok);
     }
     return post_launch(ctx);
+}
+
+// ---- TMA-pipelined one-step sweep (sweep_tma1.cuh), opt-in ---------------------------------------------------
+template <int E>
+int t1_tiles(const Geom& g) { return ceil_div(g.nz, t1::Cfg<E>::TZ) * ceil_div(g.ny, t1::Cfg<E>::TY); }
+
+template <int E>
+int t1_chunks(const wafer_ctx* ctx, int planes) {
+    const long long tiles = t1_tiles<E>(ctx->g);
+    int best_nc = 1;
+    double best_cost = 1e300;
+    for (int nc = 1; nc <= std::min(planes, 64); ++nc) {
+        const double cost = (double)ceil_div(tiles * nc, ctx->sm_count) * ((double)ceil_div(planes, nc) + 2.0 * E);
+        if (cost < best_cost * 0.999) { best_cost = cost; best_nc = nc; }
+    }
+    return best_nc;
+}
+
+template <int E>
+int init_t1_e(wafer_ctx* ctx) {
+    TRY(make_tensor_map(ctx, &ctx->t1_psi[0], ctx->psi[0], t1::Cfg<E>::R0));
+    TRY(make_tensor_map(ctx, &ctx->t1_psi[1], ctx->psi[1], t1::Cfg<E>::R0));
+    TRY(make_tensor_map(ctx, &ctx->t1_v, ctx->v, t1::Cfg<E>::TY));
+    CK(cudaFuncSetAttribute(t1::sweep_tma1_kernel<E, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(t1::Smem<E>)));
+    CK(cudaFuncSetAttribute(t1::sweep_tma1_kernel<E, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(t1::Smem<E>)));
+    return WAFER_OK;
+}
+
+int init_t1(wafer_ctx* ctx) {
+    ctx->use_t1 = false;
+    if (!ctx->onfly || !(ctx->p.flags & WAFER_FLAG_TMA_ONE_STEP)) return WAFER_OK;
+    if (ctx->p.ext == 1) TRY(init_t1_e<1>(ctx));
+    else if (ctx->p.ext == 2) TRY(init_t1_e<2>(ctx));
+    else TRY(init_t1_e<3>(ctx));
+    const double den = denominator(ctx);
+    ctx->den_ok = (den > 7.888609052210118e-31 && den < 1.2676506002282294e30) ? 1 : 0;
+    ctx->use_t1 = true;
+    return WAFER_OK;
+}
+
+template <int E>
+int launch_sweep_t1(wafer_ctx* ctx, int src, int xb, int xe, bool norm, cudaStream_t st) {
+    if (xe <= xb) return WAFER_OK;
+    const Geom& g = ctx->g;
+    const int planes = xe - xb, chunk = ceil_div(planes, t1_chunks<E>(ctx, planes));
+    dim3 grid(ceil_div(g.nz, t1::Cfg<E>::TZ), ceil_div(g.ny, t1::Cfg<E>::TY), ceil_div(planes, chunk));
+    const size_t smem = sizeof(t1::Smem<E>);
+    if (norm)
+        t1::sweep_tma1_kernel<E, true><<<grid, t1::Cfg<E>::THREADS, smem, st>>>(ctx->t1_psi[src], ctx->t1_v, ctx->psi[src ^ 1], g, xb, xe,
+                                                                               chunk, ctx->p.dt, denominator(ctx), ctx->den_ok, ctx->partials);
+    else
+        t1::sweep_tma1_kernel<E, false><<<grid, t1::Cfg<E>::THREADS, smem, st>>>(ctx->t1_psi[src], ctx->t1_v, ctx->psi[src ^ 1], g, xb, xe,
+                                                                                chunk, ctx->p.dt, denominator(ctx), ctx->den_ok, ctx->partials);
+    return post_launch(ctx);
+}
+
+template <int E>
+int t1_blocks(const wafer_ctx* ctx, int xb, int xe) {
+    const int planes = xe - xb, chunk = ceil_div(planes, t1_chunks<E>(ctx, planes));
+    return t1_tiles<E>(ctx->g) * ceil_div(planes, chunk);
+}
+
+int sweep_blocks(const wafer_ctx* ctx, int xb, int xe) {
+    if (!ctx->use_t1) return simple_blocks(ctx, xb, xe);
+    return ctx->p.ext == 1 ? t1_blocks<1>(ctx, xb, xe) : (ctx->p.ext == 2 ? t1_blocks<2>(ctx, xb, xe) : t1_blocks<3>(ctx, xb, xe));
+}
+
+// one lattice step cur -> nxt for planes [xb, xe): TMA-pipelined kernel when enabled, register-queue kernel otherwise
+int launch_sweep(wafer_ctx* ctx, const double* cur, double* nxt, int xb, int xe, bool norm, long long part_off,
+                 cudaStream_t st) {
+    if (!ctx->use_t1) return launch_sweep_plain(ctx, cur, nxt, xb, xe, norm, part_off, st);
+    const int src = cur == ctx->psi[0] ? 0 : 1;
+    if (nxt != ctx->psi[src ^ 1]) { ctx->err = "internal: sweep buffers are not the ping-pong pair"; return WAFER_ERR_INVALID; }
+    switch (ctx->p.ext) {
+        case 1: return launch_sweep_t1<1>(ctx, src, xb, xe, norm, st);
+        case 2: return launch_sweep_t1<2>(ctx, src, xb, xe, norm, st);
+        default: return launch_sweep_t1<3>(ctx, src, xb, xe, norm, st);
+    }
 }
 
 // ---- inter-GPU ordering for the fused halo: monotone pass counters in peer-visible memory ------------------
@@ -495,7 +586,8 @@ int create_impl(const wafer_params* params, wafer_ctx* ctx) {
     TRY(alloc_field(ctx, &ctx->psi[1]));
     TRY(alloc_field(ctx, &ctx->v));
     const long long nb = std::max<long long>(
-        {(long long)sweep_blocks(ctx, 0, g.L) + 4 * sweep_blocks(ctx, 0, g.e),
+        {(long long)simple_blocks(ctx, 0, g.L) + 4 * simple_blocks(ctx, 0, g.e),
+         (long long)ceil_div(g.nz, 56) * ceil_div(g.ny, 32) * std::min(g.L, 64),  // TMA one-step kernel: tiles x chunks
          (long long)ceil_div(g.nz, SW_BX) * ceil_div(g.ny, SW_BY) * ceil_div(g.L, SW_XCH), (long long)ctx->sm_count * 8});
     ctx->partials_cap = nb * 4;
     CK(cudaMalloc(&ctx->partials, ctx->partials_cap * sizeof(double)));
@@ -504,6 +596,7 @@ int create_impl(const wafer_params* params, wafer_ctx* ctx) {
     CK(cudaMallocHost(&ctx->h_scal, SL_COUNT * sizeof(double)));
     CK(cudaMalloc(&ctx->ring_flag, sizeof(int)));
     TRY(init_tb(ctx));
+    TRY(init_t1(ctx));
 
     if (ctx->world > 1) {
         if (!p.nccl_id) { ctx->err = "world > 1 needs the 128-byte nccl_id of rank 0"; return WAFER_ERR_INVALID; }
@@ -1057,7 +1150,8 @@ int wafer_selftest_division(wafer_ctx* ctx, double den, uint64_t n, uint64_t see
 
 const char* wafer_sweep_variant(const wafer_ctx* ctx) {
     if (!ctx) return "";
-    if (ctx->use_tb) return ctx->p2p ? "tb2-tma/V-onfly+p2p-halo" : "tb2-tma/V-onfly";
+    if (ctx->use_tb) return ctx->p2p ? "tb2-tma/V-onfly+p2p-halo" : (ctx->use_t1 ? "tb2-tma/V-onfly+tma1" : "tb2-tma/V-onfly");
+    if (ctx->use_t1) return "tma1/V-onfly";
     return ctx->onfly ? "simple-regqueue/V-onfly" : "simple-regqueue/AB-arrays";
 }
 
