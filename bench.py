@@ -202,7 +202,7 @@ def ncu_traffic(variant, updates_per_launch):
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             for rec in json.load(f):
-                if rec["variant"] == variant:
+                if variant.startswith(rec["variant"]):
                     return rec["dram_bytes_per_update"] * updates_per_launch, rec["note"]
     except Exception:
         pass

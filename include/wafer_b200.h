@@ -45,7 +45,8 @@ typedef enum {
 
 /* flags */
 #define WAFER_FLAG_AB_ARRAYS 0x1u   /* keep A and B as arrays (32 B/update) instead of recomputing them from V in the sweep */
-#define WAFER_FLAG_TMA_ONE_STEP 0x8u /* one-step sweeps (5/7-point, excited states, odd tail) through the TMA-pipelined kernel  */
+#define WAFER_FLAG_TMA_ONE_STEP 0x8u /* one-step sweeps (5/7-point, excited states, odd tail) through the TMA-pipelined kernel;
+                                        already the default when world == 1 and WAFER_FLAG_SIMPLE_SWEEP is not set */
 #define WAFER_FLAG_SIMPLE_SWEEP 0x4u /* force the plain register-queue sweep (no TMA pipeline, one step per pass)          */
 
 typedef struct {

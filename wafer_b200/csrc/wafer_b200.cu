@@ -278,7 +278,11 @@ int init_t1_e(wafer_ctx* ctx) {
 
 int init_t1(wafer_ctx* ctx) {
     ctx->use_t1 = false;
-    if (!ctx->onfly || !(ctx->p.flags & WAFER_FLAG_TMA_ONE_STEP)) return WAFER_OK;
+    // default on a single GPU (validated bit-for-bit there, 13-24 % faster for 5/7-point, profiles/r1_tma1_one_step.md);
+    // multi-rank contexts keep the register-queue kernel for their one-step passes unless the flag asks for it
+    const bool asked = (ctx->p.flags & WAFER_FLAG_TMA_ONE_STEP) != 0;
+    const bool by_default = ctx->world == 1 && !(ctx->p.flags & WAFER_FLAG_SIMPLE_SWEEP);
+    if (!ctx->onfly || !(asked || by_default)) return WAFER_OK;
     if (ctx->p.ext == 1) TRY(init_t1_e<1>(ctx));
     else if (ctx->p.ext == 2) TRY(init_t1_e<2>(ctx));
     else TRY(init_t1_e<3>(ctx));
