@@ -4,13 +4,16 @@
   python bench.py --gpus N --steps K --warmup W          # B200 arm (this repo's CUDA path)
   python bench.py --impl reference --gpus N ...          # reference arm: the CPU restatement of the
                                                          # reference's rayon path on the host cores
+  python bench.py --workload C5 --gpus N ...             # weak-scaling config (2048 x 2048 x 256 per GPU)
 
-Workload (BASELINE.json configs[3]): 1024^3, ThreePoint, gen_potential.py's Poschl-Teller potential, Boolean
-initial condition, ground state; x-slab decomposed over N GPUs of one box (strong scaling).  One "step" is one
-`evolve(wnum=0, screen_update)` call = SWEEPS lattice sweeps (grid.rs:544-687; default 1000 = wafer.yaml:98).  `value` counts
-nx*ny*nz*SWEEPS*K updates over the max-over-ranks device time; `e2e` adds, every step, the host->device copy of
-psi from pinned memory before evolve, one observables check (grid.rs:127-135) and the device->host copy of the evolved
-psi after it (what a stateless drop-in of the reference's loop body has to do).  Prints ONE JSON line on rank 0.
+Workload C4 (BASELINE.json configs[3], the default): 1024^3, ThreePoint, gen_potential.py's Poschl-Teller
+potential, Boolean initial condition, ground state; x-slab decomposed over N GPUs of one box (strong scaling).
+One "step" is one `evolve(wnum=0, screen_update)` call = SWEEPS lattice sweeps (grid.rs:544-687; default 1000 =
+wafer.yaml:98).  `value` counts nx*ny*nz*SWEEPS*K updates over the max-over-ranks device time; `e2e` adds, every
+step, the host->device copy of psi before evolve, one observables check (grid.rs:127-135) and the device->host copy
+of the evolved psi after it (what a stateless drop-in of the reference's loop body has to do).  `parity` compares
+the measured path bit-for-bit with an independent path of the same library (N = 1: the one-step register-queue
+kernel; N > 1: a single-GPU run of the whole lattice) through wafer_phi_checksum.  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -32,7 +35,9 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--grid", type=int, default=1024, help="lattice edge N (N^3 work sites)")
+    ap.add_argument("--workload", default="C4", choices=["C4", "C5"],
+                    help="C4: 1024^3 Poschl-Teller, strong scaling (default); C5: 2048 x 2048 x (256 per GPU) harmonic, weak scaling")
+    ap.add_argument("--grid", type=int, default=0, help="lattice edge N (N^3 work sites); default from --workload")
     ap.add_argument("--nx", type=int, default=0,
                     help="x extent (the decomposed axis) if not N: e.g. --grid 2048 --nx 256 is one GPU's share of C5")
     ap.add_argument("--sweeps", type=int, default=1000,
@@ -43,14 +48,38 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-512", action="store_true")
-    ap.add_argument("--cpu-grid", type=int, default=512)
-    return ap.parse_args()
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--parity-sweeps", type=int, default=200)
+    ap.add_argument("--cpu-grid", type=int, default=512, help="edge of the CPU sample lattice when the full one does not fit")
+    ap.add_argument("--cpu-lattice", default="auto", choices=["auto", "sample"],
+                    help="reference arm: auto = the workload's own lattice when 1.5x its five fields fit in free host memory")
+    a = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1")) if a.impl == "b200" else max(a.gpus, 1)
+    if a.workload == "C5":
+        a.grid = a.grid or 2048
+        a.nx = a.nx or 256 * world
+        a.potential, a.scaling = "Harmonic", "weak"
+    else:
+        a.grid = a.grid or 1024
+        a.potential, a.scaling = "PoschlTeller", "strong"
+    return a
 
 
-def physical_params(n):
-    """dn, dt, mass for the workload: box of width 10.24 like BASELINE C4 (dn 0.01 at 1024), dt = dn^2/3.33."""
+def physical_params(args, n):
+    """dn, dt, mass.  C4: box of width 10.24 (dn 0.01 at 1024), dt = 0.3 dn^2; C5: SURVEY §8(d) dn 0.005, dt 8e-6."""
+    if args.workload == "C5" and n == args.grid:
+        return 0.005, 8e-6, 1.0
     dn = 10.24 / n
     return dn, 0.3 * dn * dn, 1.0
+
+
+def physical_cores():
+    """the reference sizes its rayon pool with num_cpus::get_physical() (main.rs:190-192)"""
+    try:
+        import psutil
+        return psutil.cpu_count(logical=False) or os.cpu_count() or 1
+    except Exception:
+        return os.cpu_count() or 1
 
 
 # ------------------------------------------------------------------------------------------------- clocks
@@ -97,48 +126,76 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------- CPU arm
-def cpu_arm(args, steps, warmup, all_threads=True, budget_s=20.0):
+def cpu_arm(args, steps, warmup, budget_s, full_lattice):
     """The reference's CPU path (its Rust cannot be built here — SURVEY F2/F3 — so: the C++ restatement with the
-    reference's own pass structure, oracle/wafer_oracle.cpp) timed on the host cores on a bounded sample."""
+    reference's own pass structure, oracle/wafer_oracle.cpp) timed on the host's physical cores on a bounded sample:
+    each step is a few of the workload's `sweeps` sweeps.  full_lattice: use the workload's real lattice when host
+    memory allows (5 fields of it), else a --cpu-grid^3 sub-lattice; the choice is written into `sample`."""
+    import numpy as np
+
     from oracle import binding as oracle
-    n = args.cpu_grid
-    dn, dt, mass = physical_params(args.grid)
+    n = args.grid
+    nx = args.nx or n
+    need = 5.2 * nx * n * n * 8
+    avail = 0
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        pass
+    if not full_lattice or args.cpu_lattice == "sample" or avail < need * 1.5:
+        nx = n = args.cpu_grid
+    dn, dt, mass = physical_params(args, args.grid)
     ext = {"ThreePoint": 1, "FivePoint": 2, "SevenPoint": 3}[args.stencil]
-    cores = os.cpu_count() or 1
-    if all_threads:
-        oracle.set_num_threads(cores)
-    g = oracle.make_grid(n, n, n, ext=ext, dn=dn, dt=dt, mass=mass)
-    v = oracle.potential(g, "PoschlTeller")
+    cores = physical_cores()
+    oracle.set_num_threads(cores)
+    g = oracle.make_grid(nx, n, n, ext=ext, dn=dn, dt=dt, mass=mass)
+    v = oracle.potential(g, args.potential)
     a, b = oracle.build_ab(v, dt)
+    del v
     phi = oracle.initial_condition(g, "Boolean")
+    work = np.zeros(g.work_shape)  # grid.rs:560, allocated once per 1000-sweep evolve call in the reference
     t0 = time.perf_counter()
-    oracle.evolve(g, phi, a, b, 1)
-    t1 = time.perf_counter() - t0
+    oracle.evolve(g, phi, a, b, 1, work=work)   # also faults the pages in
+    oracle.evolve(g, phi, a, b, 1, work=work)
+    t1 = (time.perf_counter() - t0) / 2
     per_step = max(1, min(50, int(budget_s / max(steps + warmup, 1) / max(t1, 1e-3))))
     for _ in range(warmup):
-        oracle.evolve(g, phi, a, b, per_step)
-    t0 = time.perf_counter()
+        oracle.evolve(g, phi, a, b, per_step, work=work)
+    times = []
     for _ in range(steps):
-        oracle.evolve(g, phi, a, b, per_step)
-    el = time.perf_counter() - t0
-    glups = n ** 3 * per_step * steps / el / 1e9
-    return {"value": glups, "unit": "GLUPS", "cores": oracle.num_threads(), "kind": "port",
-            "sample": "%d^3 sub-lattice of the workload, %d steps x %d sweeps of oracle evolve (stencil into work + "
-                      "copy-back, grid.rs:560-673), OpenMP on %d threads" % (n, steps, per_step, oracle.num_threads()),
-            "ms_per_step": el / steps * 1e3, "sweeps_per_step": per_step}
+        t0 = time.perf_counter()
+        oracle.evolve(g, phi, a, b, per_step, work=work)
+        times.append(time.perf_counter() - t0)
+    el = sum(times)
+    sites_ = nx * n * n
+    rate = lambda t: sites_ * per_step / t / 1e9
+    ts = sorted(times)
+    return {"value": sites_ * per_step * steps / el / 1e9, "unit": "GLUPS", "cores": oracle.num_threads(), "kind": "port",
+            "sample": "%dx%dx%d lattice (%s), %d steps x %d of the step's %d sweeps of oracle evolve (stencil into work + "
+                      "copy-back, grid.rs:560-673; work array pre-allocated as the reference amortises it over the whole "
+                      "call), OpenMP on %d threads = physical cores (main.rs:190-192)"
+                      % (nx, n, n, "the workload's own lattice" if (nx, n) == (args.nx or args.grid, args.grid) else "sub-lattice of the workload: host memory",
+                         steps, per_step, args.sweeps, oracle.num_threads()),
+            "spread": {"min": rate(ts[-1]), "median": rate(ts[len(ts) // 2]), "max": rate(ts[0]), "repetitions": len(ts)},
+            "ms_per_step": el / steps * 1e3, "sweeps_per_step": per_step, "lattice": [nx, n, n]}
 
 
 def reference_main(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb = cpu_arm(args, args.steps, args.warmup, all_threads=True, budget_s=60.0)
+    cb = cpu_arm(args, args.steps, args.warmup, budget_s=75.0, full_lattice=True)
+    cfg = workload_config(args, args.gpus)
+    cfg["reference_sample"] = {"lattice": cb["lattice"], "sweeps_per_step": cb["sweeps_per_step"],
+                               "note": "a CPU step is a bounded sample (sweeps_per_step of the workload's %d sweeps per "
+                                       "step); the value is a rate, so it compares with the GPU arm's" % args.sweeps}
     line = {
         "impl": "reference", "metric": "f64 lattice updates/s", "value": cb["value"], "unit": "GLUPS",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, args.gpus),
-        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": cfg,
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "spread")},
         "e2e": {"value": cb["value"], "unit": "GLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -148,8 +205,9 @@ def reference_main(args):
 def workload_config(args, world):
     n = args.grid
     nx = args.nx or n
-    return {"workload": "C4: %dx%dx%d %s, Poschl-Teller (gen_potential.py formula, lam=6), Boolean IC, ground state; "
-                        "step = evolve(wnum=0, screen_update=%d)" % (nx, n, n, args.stencil, args.sweeps),
+    pot = {"PoschlTeller": "Poschl-Teller (gen_potential.py formula, lam=6)", "Harmonic": "Harmonic (potential.rs:270-274)"}[args.potential]
+    return {"workload": "%s: %dx%dx%d %s, %s, Boolean IC, ground state; step = evolve(wnum=0, screen_update=%d)"
+                        % (args.workload, nx, n, n, args.stencil, pot, args.sweeps),
             "grid": [nx, n, n], "stencil": args.stencil, "sweeps_per_step": args.sweeps,
             "decomposition": ("x-slab x%d, halo: %s" % (world, "NCCL send/recv" if args.no_p2p else "fused peer stores (CUDA IPC over NVLink)"))
             if world > 1 else "single GPU",
@@ -157,7 +215,7 @@ def workload_config(args, world):
 
 
 # ------------------------------------------------------------------------------------------------- B200 arm
-def measure(lat, args, n, world, dist, steps, warmup, sampler=None):
+def measure(lat, args, nsites, dist, steps, warmup, sampler=None):
     """W untimed + K timed evolve(0, sweeps) calls, device-timed with CUDA events on the library's stream."""
     for _ in range(warmup):
         lat.evolve(0, args.sweeps)
@@ -180,12 +238,8 @@ def measure(lat, args, n, world, dist, steps, warmup, sampler=None):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.barrier()
         ms = float(t.item())
-    glups = sites(args, n) * args.sweeps * steps / (ms * 1e-3) / 1e9
+    glups = nsites * args.sweeps * steps / (ms * 1e-3) / 1e9
     return glups, ms, launches, clocks
-
-
-def sites(args, n):
-    return (args.nx or n) * n * n if n == args.grid else n ** 3
 
 
 def hbm_peak():
@@ -209,9 +263,104 @@ def ncu_traffic(variant, updates_per_launch):
     return None, None
 
 
-def b200_main(args):
+def connect_p2p(lat, dist, rank, world):
+    """fused halo: boundary CTAs store into the neighbours' ghost planes through CUDA-IPC mapped peer memory"""
+    import torch
+    mine = torch.tensor(list(lat.p2p_export()), dtype=torch.uint8, device="cuda")
+    blobs = [torch.zeros(192, dtype=torch.uint8, device="cuda") for _ in range(world)]
+    dist.all_gather(blobs, mine)
+    blobs = [bytes(b.cpu().tolist()) for b in blobs]
+    lat.p2p_connect(blobs[rank - 1] if rank > 0 else None, blobs[rank + 1] if rank < world - 1 else None)
+
+
+def parity_leg(lat, args, shape, phys, local_rank, rank, world, dist):
+    """Bit-for-bit comparison of the measured path with an independent one, at the workload's full size.
+    N = 1: the time-tiled TMA kernel against the plain one-step register-queue kernel (WAFER_FLAG_SIMPLE_SWEEP).
+    N > 1: this rank's slab of the decomposed run against the same planes of a single-GPU run of the WHOLE lattice
+    (every rank runs its own copy on its own GPU), after `parity_sweeps` sweeps — long enough for the ranks to
+    drift apart — followed by one observables check on both (the check reads the ghost planes)."""
+    import wafer_b200
+    dn, dt, mass = phys
+    s = args.parity_sweeps
+    other_flags = wafer_b200.FLAG_SIMPLE_SWEEP if world == 1 else args.flags
+    x0, x1 = lat.slab
+    lat.generate_potential(args.potential)
+    lat.set_initial_conditions("Boolean")
+    lat.check(0)
+    lat.evolve(0, s)
+    mine = lat.phi_checksum(x0, x1)
+    o_mine = lat.check(0)
+    with wafer_b200.Lattice(shape, args.stencil, dn=dn, dt=dt, mass=mass, device=local_rank, flags=other_flags) as ref:
+        ref.generate_potential(args.potential)
+        ref.set_initial_conditions("Boolean")
+        ref.check(0)
+        ref.evolve(0, s)
+        theirs = ref.phi_checksum(x0, x1)
+        o_ref = ref.check(0)
+        ref_variant = ref.sweep_variant
+    e_mine, e_ref = o_mine["energy"] / o_mine["norm2"], o_ref["energy"] / o_ref["norm2"]
+    bit = mine == theirs
+    rel = abs(e_mine - e_ref) / abs(e_ref)
+    if dist is not None:
+        import torch
+        t = torch.tensor([0.0 if bit else 1.0, rel], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        bit, rel = bool(t[0].item() == 0.0), float(t[1].item())
+    return {"psi_bitwise_equal": bit, "energy_rel_diff": rel, "energy": e_mine, "sweeps": s,
+            "against": ("single-GPU run of the whole lattice (%s) on every rank's GPU, compared per slab" % ref_variant) if world > 1
+            else "one-step register-queue kernel (%s) on the same GPU" % ref_variant,
+            "method": "wafer_phi_checksum (position-sensitive 128-bit sum/xor of per-site hashes) after evolve(0, %d); "
+                      "energy from wafer_check on both; tolerance 1e-9 relative (north_star)" % s,
+            "ok": bool(bit and rel <= 1e-9)}
+
+
+def e2e_leg(lat, args, nsites, world, dist, pinned):
+    """set_phi_owned(host) -> evolve -> check -> get_phi_slab(host) per step; the state travels through HOST buffers.
+    pinned = False: ordinary pageable numpy arrays, which is what the reference's Array3::as_ptr() would hand over."""
     import numpy as np
 
+    import wafer_b200
+    q0, q1 = lat.slab_planes(1)
+    shp = (q1 - q0,) + lat.padded_shape[1:]
+    if pinned:
+        h_in, h_out = wafer_b200.pinned_empty(shp), wafer_b200.pinned_empty(shp)
+    else:
+        h_in, h_out = np.empty(shp), np.empty(shp)
+    lat.get_phi_slab(h_in)
+    e_steps, e_warm = (min(args.steps, 3), 1) if pinned else (min(args.steps, 2), 1)
+    tot, obs = 0.0, None
+    for it in range(e_warm + e_steps):
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        lat.timer_begin()
+        lat.set_phi_owned(h_in)     # owned planes from the host; ghost planes re-fetched from the neighbours
+        lat.evolve(0, args.sweeps)
+        obs = lat.check(0)          # the loop body of grid.rs:126-221: observables + normalise, 4 scalars back to the host
+        lat.get_phi_slab(h_out)
+        ms_e = lat.timer_end()
+        wall = (time.perf_counter() - t0) * 1e3
+        ms_e = max(ms_e, wall)      # the copies synchronise the host: count whichever clock saw more
+        if dist is not None:
+            import torch
+            t = torch.tensor([ms_e], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_e = float(t.item())
+        if it >= e_warm:
+            tot += ms_e
+        h_in, h_out = h_out, h_in   # the evolved state is the next step's input
+    out = {"value": nsites * args.sweeps * e_steps / (tot * 1e-3) / 1e9, "unit": "GLUPS",
+           "h2d_bytes_per_step": int(h_in.size * 8 * world), "d2h_bytes_per_step": int(h_out.size * 8 * world),
+           "steps": e_steps, "ms_per_step": tot / e_steps, "host_memory": "pinned (wafer_host_alloc)" if pinned else "pageable (numpy)",
+           "call": "wafer_set_phi_owned(host) -> wafer_evolve(0, %d) -> wafer_check(0) -> wafer_get_phi_slab(host)" % args.sweeps,
+           "last_energy": obs["energy"] / obs["norm2"], "checks_seen": e_warm + e_steps}
+    if pinned:
+        wafer_b200.pinned_free(h_in)
+        wafer_b200.pinned_free(h_out)
+    return out
+
+
+def b200_main(args):
     import wafer_b200
 
     rank = int(os.environ.get("RANK", "0"))
@@ -234,24 +383,25 @@ def b200_main(args):
         sys.stderr.write("warning: --gpus %d but WORLD_SIZE %d; using WORLD_SIZE\n" % (args.gpus, world))
 
     n = args.grid
-    dn, dt, mass = physical_params(n)
-    nsites = sites(args, n)
-    lat = wafer_b200.Lattice((args.nx or n, n, n), args.stencil, dn=dn, dt=dt, mass=mass, device=local_rank, rank=rank, world=world,
+    shape = (args.nx or n, n, n)
+    phys = physical_params(args, n)
+    dn, dt, mass = phys
+    nsites = shape[0] * n * n
+    lat = wafer_b200.Lattice(shape, args.stencil, dn=dn, dt=dt, mass=mass, device=local_rank, rank=rank, world=world,
                              nccl_id=nccl_id, flags=args.flags)
     if world > 1 and not args.no_p2p:
-        # fused halo: boundary CTAs store into the neighbours' ghost planes through CUDA-IPC mapped peer memory
-        import torch
-        mine = torch.tensor(list(lat.p2p_export()), dtype=torch.uint8, device="cuda")
-        blobs = [torch.zeros(192, dtype=torch.uint8, device="cuda") for _ in range(world)]
-        dist.all_gather(blobs, mine)
-        blobs = [bytes(b.cpu().tolist()) for b in blobs]
-        lat.p2p_connect(blobs[rank - 1] if rank > 0 else None, blobs[rank + 1] if rank < world - 1 else None)
-    lat.generate_potential("PoschlTeller")
+        connect_p2p(lat, dist, rank, world)
+
+    parity = None
+    if not args.no_parity:
+        parity = parity_leg(lat, args, shape, phys, local_rank, rank, world, dist)
+
+    lat.generate_potential(args.potential)
     lat.set_initial_conditions("Boolean")
     lat.check(0)  # normalise once so that thousands of sweeps stay in range
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    glups, ms, launches, clocks = measure(lat, args, n, world, dist, args.steps, args.warmup, sampler)
+    glups, ms, launches, clocks = measure(lat, args, nsites, dist, args.steps, args.warmup, sampler)
     sweeps_total = args.sweeps * args.steps
 
     peak, peak_src = hbm_peak()
@@ -271,81 +421,43 @@ def b200_main(args):
                 "dram_frac_of_peak": (traffic / (launch_ms * 1e-3) / 1e9 / peak) if traffic else None,
                 "frac_of_nominal_8TBps": achieved / 8000.0}
 
-    # ---- e2e: host buffers in and out of every step (pinned), through the C ABI
+    # ---- e2e: host buffers in and out of every step, through the C ABI
     e2e = None
     if not args.no_e2e:
-        p0, p1 = lat.slab_planes(0)
-        q0, q1 = lat.slab_planes(1)
-        shape_yz = lat.padded_shape[1:]
-        planes = max(p1 - p0, q1 - q0)
-        host = wafer_b200.pinned_empty((planes,) + shape_yz)
-        h_in = host[:p1 - p0]
-        h_out = host[:q1 - q0]
-        # the chunk this rank would hold of the global array: current psi + ghost planes (zero ring at the ends)
-        h_in[...] = 0.0
-        tmp = lat.get_phi_slab()
-        h_in[q0 - p0:q0 - p0 + (q1 - q0)] = tmp
-        del tmp
-        e_steps, e_warm = min(args.steps, 3), 1
-        tot = 0.0
-        for it in range(e_warm + e_steps):
-            if dist is not None:
-                dist.barrier()
-            t0 = time.perf_counter()
-            lat.timer_begin()
-            lat.set_phi_slab(h_in)
-            lat.evolve(0, args.sweeps)
-            obs = lat.check(0)  # the loop body of grid.rs:126-221: observables + normalise, 4 scalars back to the host
-            lat.get_phi_slab(h_out)
-            ms_e = lat.timer_end()
-            wall = (time.perf_counter() - t0) * 1e3
-            ms_e = max(ms_e, wall)  # the copies synchronise the host: count whichever clock saw more
-            if dist is not None:
-                import torch
-                t = torch.tensor([ms_e], dtype=torch.float64, device="cuda")
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                ms_e = float(t.item())
-            if it >= e_warm:
-                tot += ms_e
-            # feed the evolved state back in (keeps the ring zero and the values finite)
-            h_in[q0 - p0:q0 - p0 + (q1 - q0)] = h_out
-        e2e = {"value": nsites * args.sweeps * e_steps / (tot * 1e-3) / 1e9, "unit": "GLUPS",
-               "h2d_bytes_per_step": int(h_in.size * 8 * world), "d2h_bytes_per_step": int(h_out.size * 8 * world),
-               "steps": e_steps, "ms_per_step": tot / e_steps,
-               "call": "wafer_set_phi_slab(pinned) -> wafer_evolve(0, %d) -> wafer_check(0) -> wafer_get_phi_slab(pinned)"
-                       % args.sweeps, "last_energy": obs["energy"] / obs["norm2"]}
-        wafer_b200.pinned_free(host)
+        e2e = e2e_leg(lat, args, nsites, world, dist, pinned=True)
+        e2e["pageable"] = {k: v for k, v in e2e_leg(lat, args, nsites, world, dist, pinned=False).items()
+                           if k in ("value", "unit", "ms_per_step", "steps", "host_memory", "last_energy")}
 
     info = lat.device_info()
     variant = lat.sweep_variant
     lat.close()
 
     extra = {}
-    if rank == 0 and world == 1 and not args.no_512 and n != 512 and not args.nx:
+    if rank == 0 and world == 1 and not args.no_512 and n != 512 and not args.nx and args.workload == "C4":
         # BASELINE metric's other quoted point: 512^3 on one GPU
         a2 = argparse.Namespace(**vars(args))
         a2.grid = 512
-        dn2, dt2, m2 = physical_params(512)
+        dn2, dt2, m2 = physical_params(a2, 512)
         with wafer_b200.Lattice((512,) * 3, args.stencil, dn=dn2, dt=dt2, mass=m2, device=local_rank, flags=args.flags) as l2:
-            l2.generate_potential("PoschlTeller")
+            l2.generate_potential(args.potential)
             l2.set_initial_conditions("Boolean")
             l2.check(0)
-            g512, ms512, _, _ = measure(l2, a2, 512, 1, None, max(args.steps, 3), 3)
+            g512, ms512, _, _ = measure(l2, a2, 512 ** 3, None, max(args.steps, 3), 3)
         extra["glups_512cubed_1gpu"] = g512
         extra["hbm_frac_512cubed"] = g512 * BYTES_PER_UPDATE / peak
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = cpu_arm(args, steps=2, warmup=1, all_threads=True, budget_s=15.0)
-        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        cpu = cpu_arm(args, steps=3, warmup=1, budget_s=15.0, full_lattice=False)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "spread")}
 
     if rank == 0:
         line = {
             "metric": "f64 lattice updates/s", "value": glups, "unit": "GLUPS", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "device": info["name"], "sweep_variant": variant, "extra": extra,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "parity": parity, "gpu_launches": int(launches),
+            "clocks": clocks, "device": info["name"], "sweep_variant": variant, "extra": extra,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:

@@ -96,6 +96,10 @@ int wafer_get_phi(wafer_ctx *ctx, double *phi_padded);
 int wafer_slab_planes(const wafer_ctx *ctx, int32_t which, uint64_t *p0, uint64_t *p1);
 int wafer_set_phi_slab(wafer_ctx *ctx, const double *chunk);
 int wafer_get_phi_slab(wafer_ctx *ctx, double *chunk);
+/* The inverse of wafer_get_phi_slab: `chunk` is the which=1 run (owned planes, plus the outer ring planes on the first /
+   last rank).  The ghost planes are then fetched from the x-neighbours, so this is a COLLECTIVE call when world > 1
+   (every rank calls it, like the check at grid.rs:127).  get_phi_slab -> set_phi_owned round-trips the state. */
+int wafer_set_phi_owned(wafer_ctx *ctx, const double *chunk);
 int wafer_push_lower(wafer_ctx *ctx, const double *q_padded);     /* input::load_wavefunctions (input.rs:487-505)            */
 int wafer_push_lower_from_phi(wafer_ctx *ctx);                    /* w_store.push(phi)          (grid.rs:241)                */
 int wafer_get_lower(wafer_ctx *ctx, uint32_t idx, double *q_padded);
@@ -146,6 +150,14 @@ int wafer_p2p_connect(wafer_ctx *ctx, const uint8_t *lower, const uint8_t *upper
 /* self-test of the sweep's division by the loop-invariant denominator: compares it bit-for-bit with IEEE
    division on n pseudo-random operands (every exponent, zeros, denormals, NaN/Inf); *mismatches must be 0 */
 int wafer_selftest_division(wafer_ctx *ctx, double den, uint64_t n, uint64_t seed, uint64_t *mismatches);
+/* Position-sensitive, slab-independent checksum of the work-area sites of GLOBAL work planes [x_begin, x_end) that this
+   rank owns: out[0] = wrapping sum, out[1] = xor of mix64(bits(psi) + c * (global site index + 1)).  Add the out[0]s and
+   xor the out[1]s of all ranks to get the checksum of the union; equal checksums <=> bit-identical wavefunctions (up to
+   2^-64 collisions).  This is how multi-GPU runs are compared bit-for-bit with a single-GPU run at full size. */
+int wafer_phi_checksum(wafer_ctx *ctx, uint64_t x_begin, uint64_t x_end, uint64_t out[2]);
+/* Fault injection for the multi-GPU ordering tests: stall this rank's halo stream by `nanoseconds` (<= 1e9) before
+   every boundary pass of wafer_evolve, so that its x-neighbours run ahead.  0 switches it off. */
+int wafer_debug_halo_delay(wafer_ctx *ctx, uint64_t nanoseconds);
 const char *wafer_version(void);
 const char *wafer_sweep_variant(const wafer_ctx *ctx); /* name of the sweep kernel variant in use */
 

@@ -76,6 +76,7 @@ def lib():
         L.wo_normalise.argtypes = [_dp, C.c_uint64, C.c_double]
         L.wo_orthogonalise.argtypes = [_dp, C.POINTER(_dp), C.c_uint32, C.c_uint64, C.c_uint64]
         L.wo_evolve.argtypes = [gp, _dp, _dp, _dp, C.POINTER(_dp), C.c_uint32, C.c_uint64]
+        L.wo_evolve_ws.argtypes = [gp, _dp, _dp, _dp, C.POINTER(_dp), C.c_uint32, C.c_uint64, _dp]
         L.wo_observables.argtypes = [gp, _dp, _dp, C.c_int, C.c_double, _dp, _dp]
         L.wo_potential.restype = C.c_int
         L.wo_potential.argtypes = [gp, C.c_int, C.c_double, _dp]
@@ -174,9 +175,15 @@ def orthogonalise(w, lowers, wnum=None):
     lib().wo_orthogonalise(_p(w), _lowers(lowers), wnum, w.size, w.shape[0])
 
 
-def evolve(g, phi, a, b, steps, lowers=(), wnum=None):
+def evolve(g, phi, a, b, steps, lowers=(), wnum=None, work=None):
+    """work: optional pre-allocated work-sized scratch array (grid.rs:560); the timed baseline passes one so that a
+    bounded sample is not charged the per-call allocation the reference amortises over screen_update sweeps"""
     wnum = len(lowers) if wnum is None else wnum
-    lib().wo_evolve(C.byref(g), _p(phi), _p(a), _p(b), _lowers(lowers), wnum, steps)
+    if work is None:
+        lib().wo_evolve(C.byref(g), _p(phi), _p(a), _p(b), _lowers(lowers), wnum, steps)
+    else:
+        assert work.shape == tuple(g.work_shape)
+        lib().wo_evolve_ws(C.byref(g), _p(phi), _p(a), _p(b), _lowers(lowers), wnum, steps, _p(work))
 
 
 def observables(g, phi, v, potsub=None):

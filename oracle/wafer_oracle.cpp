@@ -340,22 +340,24 @@ void wo_orthogonalise(double* w, const double* const* lowers, uint32_t wnum, uin
 // ---------------------------------------------------------------- grid.rs:544-687
 // Same pass structure as the reference (stencil into `work`, copy back, per-step norm/normalise/GS
 // when wnum>0), so this function is also the timed CPU baseline.
-void wo_evolve(const wo_grid* g, double* phi, const double* a, const double* b, const double* const* lowers,
-               uint32_t wnum, uint64_t steps) {
+// `work` is the scratch array of grid.rs:560 (work-sized).  The reference allocates it once per evolve call, i.e. once
+// per screen_update (1000) sweeps; wo_evolve_ws lets the timed baseline hand in a pre-faulted buffer so that a bounded
+// sample of a few sweeps is not charged an allocation the real run amortises over a thousand.
+void wo_evolve_ws(const wo_grid* g, double* phi, const double* a, const double* b, const double* const* lowers,
+                  uint32_t wnum, uint64_t steps, double* work) {
     const Dims d(g);
-    std::vector<double> work(d.work());  // grid.rs:560
     uint64_t done = 0;
     for (;;) {
         switch (g->ext) {
-            case 1: sweep_into_work<1>(g, d, phi, a, b, work.data()); break;
-            case 2: sweep_into_work<2>(g, d, phi, a, b, work.data()); break;
-            default: sweep_into_work<3>(g, d, phi, a, b, work.data()); break;
+            case 1: sweep_into_work<1>(g, d, phi, a, b, work); break;
+            case 2: sweep_into_work<2>(g, d, phi, a, b, work); break;
+            default: sweep_into_work<3>(g, d, phi, a, b, work); break;
         }
         // grid.rs:666-673
 #pragma omp parallel for collapse(2) schedule(static)
         for (long long i = 0; i < (long long)d.nx; ++i)
             for (long long j = 0; j < (long long)d.ny; ++j)
-                std::memcpy(phi + d.p(i + d.e, j + d.e, d.e), work.data() + d.w(i, j, 0), d.nz * sizeof(double));
+                std::memcpy(phi + d.p(i + d.e, j + d.e, d.e), work + d.w(i, j, 0), d.nz * sizeof(double));
         if (wnum > 0) {  // grid.rs:674-681
             const double n2 = wo_norm2_work(g, phi);
             wo_normalise(phi, d.padded(), n2);
@@ -364,6 +366,13 @@ void wo_evolve(const wo_grid* g, double* phi, const double* a, const double* b, 
         done += 1;  // grid.rs:682-685: do-while, so steps==0 still performs one sweep
         if (done >= steps) break;
     }
+}
+
+void wo_evolve(const wo_grid* g, double* phi, const double* a, const double* b, const double* const* lowers,
+               uint32_t wnum, uint64_t steps) {
+    const Dims d(g);
+    std::vector<double> work(d.work());  // grid.rs:560
+    wo_evolve_ws(g, phi, a, b, lowers, wnum, steps, work.data());
 }
 
 // ---------------------------------------------------------------- grid.rs:303-445
@@ -567,6 +576,7 @@ void wo_zero_ring(const wo_grid* g, double* w) {
 int wo_initial_condition(const wo_grid* g, int kind, double* w) {
     const Dims d(g);
     if (kind < 2 || kind > 4) return 1;  // FromFile / Gaussian(thread_rng) are not reproducible here
+#pragma omp parallel for schedule(static)
     for (size_t i = 0; i < d.px; ++i)
         for (size_t j = 0; j < d.py; ++j)
             for (size_t k = 0; k < d.pz; ++k) {

@@ -87,6 +87,51 @@ def main():
         ok = ok and res["ground_bitwise"] and res["excited_l2"] < 1e-12 and res["obs_rel"] < 1e-12 and res["obs_rel_excited"] < 1e-11
         single.close()
         multi.close()
+    # ---- ordering under drift: one rank's halo stream is stalled before every boundary pass, so
+    # its neighbours run ahead.  The check after evolve reads the ghost planes (energy stencil) and normalises them in
+    # place; a second evolve then starts from those ghosts.  Everything is compared with a single-GPU run of the same
+    # lattice through the slab-independent checksum (bit-for-bit) and the observables (<= 1e-12).
+    shape = (int(os.environ.get("WAFER_DRIFT_NX", 48 * world)), 160, 192)
+    sweeps = int(os.environ.get("WAFER_DRIFT_SWEEPS", 300))
+    dn = 10.24 / shape[1]
+    kw = dict(dn=dn, dt=0.3 * dn * dn, mass=1.0, device=local)
+    single = wafer_b200.Lattice(shape, "ThreePoint", **kw)
+    multi = wafer_b200.Lattice(shape, "ThreePoint", rank=rank, world=world, nccl_id=fresh_nccl_id(), **kw)
+    if use_p2p:
+        connect(multi)
+    if rank == 1 % world:
+        multi.debug_halo_delay(int(os.environ.get("WAFER_DRIFT_DELAY_NS", 40000)))
+    x0, x1 = multi.slab
+    drift = dict(bitwise=[], obs_rel=[])
+    for lat in (single, multi):
+        lat.generate_potential("PoschlTeller")
+        lat.set_initial_conditions("Boolean")
+    norm2 = None
+    for rnd in range(3):
+        per = []
+        for lat in (single, multi):
+            if rnd == 2:
+                # the stateless drop-in round trip: owned planes out to the host and back in, ghosts re-fetched
+                lat.set_phi_owned(lat.get_phi_slab()) if lat is multi else lat.set_phi(lat.get_phi())
+            lat.evolve(0, sweeps + rnd)  # rnd = 1: odd count -> the one-step tail pass takes part too
+            ck = lat.phi_checksum(x0, x1)
+            obs = lat.compute_observables()
+            per.append((ck, obs))
+        (cs, os_), (cm, om) = per
+        drift["bitwise"].append(cs == cm)
+        drift["obs_rel"].append(max(abs(os_[k] - om[k]) / max(abs(os_[k]), 1e-300) for k in os_))
+        norm2 = os_["norm2"]  # the SAME divisor on both, so that the next round stays bit-comparable
+        single.normalise_wavefunction(norm2)
+        multi.normalise_wavefunction(norm2)
+    t = torch.tensor([float(all(drift["bitwise"])), max(drift["obs_rel"])], dtype=torch.float64, device="cuda")
+    allt = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(allt, t)
+    allt = torch.stack(allt).cpu().numpy()
+    results["drift"] = dict(shape=list(shape), sweeps=sweeps, bitwise=bool(allt[:, 0].all()), obs_rel=float(allt[:, 1].max()),
+                            final_wait=os.environ.get("WAFER_DEBUG_SKIP_FINAL_WAIT", "0") != "1")
+    ok = ok and results["drift"]["bitwise"] and results["drift"]["obs_rel"] < 1e-12
+    single.close()
+    multi.close()
     if rank == 0:
         print(json.dumps({"world": world, "ok": ok, "halo": "p2p" if use_p2p else "nccl", "results": results}), flush=True)
     dist.barrier()

@@ -13,6 +13,20 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def _gpu_present():
+    return os.path.exists("/dev/nvidiactl") or os.path.exists("/dev/nvidia0")
+
+
+def pytest_collection_modifyitems(config, items):
+    """`gpu` tests are skipped, not failed, on a machine without a CUDA device (a plain `pytest` stays green there)."""
+    if _gpu_present():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device on this machine (run with -m gpu on a B200 box)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def oracle():
     from oracle import binding

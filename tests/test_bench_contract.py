@@ -18,7 +18,7 @@ def _run(args, env=None):
 
 
 def test_reference_arm_line():
-    r = _run(["--impl", "reference", "--gpus", "1", "--steps", "2", "--warmup", "1", "--cpu-grid", "48"])
+    r = _run(["--impl", "reference", "--gpus", "1", "--steps", "2", "--warmup", "1", "--cpu-grid", "48", "--cpu-lattice", "sample"])
     assert r.returncode == 0, r.stderr
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
@@ -30,10 +30,13 @@ def test_reference_arm_line():
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sub-lattice" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "GLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "1024x1024x1024" in d["config"]["workload"] and "model" not in d["config"]
+    # the sample the CPU arm really ran is part of its config
+    assert d["config"]["reference_sample"]["lattice"] == [48, 48, 48] and cb["spread"]["repetitions"] == 2
+    assert cb["spread"]["min"] <= cb["spread"]["median"] <= cb["spread"]["max"]
 
 
 def test_reference_arm_other_ranks_do_nothing():
-    r = _run(["--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1", "--cpu-grid", "32"], env={"RANK": "1"})
+    r = _run(["--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1", "--cpu-grid", "32", "--cpu-lattice", "sample"], env={"RANK": "1"})
     assert r.returncode == 0 and r.stdout.strip() == ""
 
 

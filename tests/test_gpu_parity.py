@@ -53,6 +53,59 @@ def test_set_get_roundtrip_is_exact(wb, oracle, ext, shape):
         assert lat.num_lowers == 1 and np.array_equal(lat.get_lower(0), phi)
 
 
+def _np_checksum(phi, ext, x_begin, x_end):
+    """numpy restatement of checksum_kernel (kernels.cuh): pins the definition of wafer_phi_checksum"""
+    w = npr.work(phi, ext)
+    nx, ny, nz = w.shape
+    idx = np.arange(nx * ny * nz, dtype=np.uint64).reshape(w.shape) + np.uint64(1)
+    with np.errstate(over="ignore"):
+        z = np.ascontiguousarray(w).view(np.uint64) + np.uint64(0x9E3779B97F4A7C15) * idx
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = (z ^ (z >> np.uint64(31)))[x_begin:x_end]
+        return int(z.sum(dtype=np.uint64)), int(np.bitwise_xor.reduce(z.ravel())) if z.size else 0
+
+
+@pytest.mark.parametrize("ext", [1, 3])
+def test_phi_checksum_is_position_sensitive_and_slab_independent(wb, oracle, ext):
+    shape = (13, 10, 37)
+    g, v, phi = _rand_state(oracle, shape, ext, 21)
+    npr.work(phi, ext)[2, 3, 4] = -0.0  # bit patterns, not values
+    with wb.Lattice(shape, CD[ext], dn=g.dn, dt=g.dt, mass=g.mass) as lat:
+        lat.set_phi(phi)
+        whole = lat.phi_checksum()
+        assert whole == _np_checksum(phi, ext, 0, 13)
+        a, b = lat.phi_checksum(0, 5), lat.phi_checksum(5, 13)
+        assert a == _np_checksum(phi, ext, 0, 5)
+        assert ((a[0] + b[0]) % 2 ** 64, a[1] ^ b[1]) == whole        # any cut into slabs combines to the same value
+        assert lat.phi_checksum(4, 4) == (0, 0) and lat.phi_checksum(0, 99) == whole
+        swapped = phi.copy()
+        w = npr.work(swapped, ext)
+        w[1, 1, 1], w[1, 1, 2] = w[1, 1, 2], w[1, 1, 1]            # same multiset of values, different sites
+        lat.set_phi(swapped)
+        assert lat.phi_checksum() != whole
+        npr.work(phi, ext)[2, 3, 4] = 0.0                              # +0 instead of -0: one bit
+        lat.set_phi(phi)
+        assert lat.phi_checksum() != whole
+
+
+def test_set_phi_owned_inverts_get_phi_slab(wb, oracle):
+    """single rank: the owned run is the whole padded array; larger than one bounce buffer would be at 256^3
+    (test_sweep_bitwise_256_and_launch_count covers the multi-chunk staging path)"""
+    g, v, phi = _rand_state(oracle, (9, 12, 20), 2, 22)
+    with wb.Lattice((9, 12, 20), "FivePoint", dn=g.dn, dt=g.dt, mass=g.mass) as lat:
+        lat.set_phi(phi)
+        chunk = lat.get_phi_slab()
+        assert lat.slab_planes(1) == (0, 13) and np.array_equal(chunk, phi)
+        lat.set_phi_owned(np.ascontiguousarray(chunk * 2.0))
+        assert np.array_equal(lat.get_phi(), phi * 2.0)
+        bad = chunk.copy()
+        bad[0, 3, 3] = 1.0
+        with pytest.raises(wb.WaferError) as ei:
+            lat.set_phi_owned(bad)
+        assert ei.value.status == 5
+
+
 def test_ring_must_be_zero_and_not_ready_errors(wb, oracle):
     g, v, phi = _rand_state(oracle, (6, 6, 6), 1, 2)
     with wb.Lattice((6, 6, 6)) as lat:

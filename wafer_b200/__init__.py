@@ -226,6 +226,22 @@ class Lattice:
         self._ck(self._lib.wafer_get_phi_slab(self._h, _p(out)))
         return out
 
+    def set_phi_owned(self, chunk):
+        """inverse of get_phi_slab: owned planes in, ghost planes fetched from the neighbours (collective)"""
+        p0, p1 = self.slab_planes(1)
+        assert chunk.shape == (p1 - p0,) + self.padded_shape[1:]
+        self._ck(self._lib.wafer_set_phi_owned(self._h, _p(chunk)))
+
+    def phi_checksum(self, x_begin=0, x_end=None):
+        """(wrapping sum, xor) of the per-site hashes of global work planes [x_begin, x_end) owned by this rank"""
+        out = (C.c_uint64 * 2)()
+        self._ck(self._lib.wafer_phi_checksum(self._h, x_begin, self.size[0] if x_end is None else x_end, out))
+        return int(out[0]), int(out[1])
+
+    def debug_halo_delay(self, nanoseconds):
+        """fault injection: stall this rank's halo stream before every boundary pass (tests of the GPU-GPU ordering)"""
+        self._ck(self._lib.wafer_debug_halo_delay(self._h, int(nanoseconds)))
+
     def set_initial_conditions(self, kind):
         """config::set_initial_conditions (config.rs:577-627) evaluated on the device."""
         self._ck(self._lib.wafer_generate_initial_condition(self._h, INITIAL_CONDITIONS[kind]))

@@ -42,6 +42,7 @@ SYMBOLS = {
     "wafer_slab_planes": (C.c_int, [_ctx, C.c_int32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "wafer_set_phi_slab": (C.c_int, [_ctx, _dp]),
     "wafer_get_phi_slab": (C.c_int, [_ctx, _dp]),
+    "wafer_set_phi_owned": (C.c_int, [_ctx, _dp]),
     "wafer_push_lower": (C.c_int, [_ctx, _dp]),
     "wafer_push_lower_from_phi": (C.c_int, [_ctx]),
     "wafer_get_lower": (C.c_int, [_ctx, C.c_uint32, _dp]),
@@ -70,6 +71,8 @@ SYMBOLS = {
     "wafer_p2p_export": (C.c_int, [_ctx, C.POINTER(C.c_uint8)]),
     "wafer_p2p_connect": (C.c_int, [_ctx, C.POINTER(C.c_uint8), C.POINTER(C.c_uint8)]),
     "wafer_selftest_division": (C.c_int, [_ctx, C.c_double, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "wafer_phi_checksum": (C.c_int, [_ctx, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "wafer_debug_halo_delay": (C.c_int, [_ctx, C.c_uint64]),
     "wafer_version": (C.c_char_p, []),
     "wafer_sweep_variant": (C.c_char_p, [_ctx]),
 }

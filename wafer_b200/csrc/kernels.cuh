@@ -373,26 +373,28 @@ __global__ void __launch_bounds__(EW_THREADS)
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Host layout <-> device layout.  `host` points at padded plane hp0 of the reference array (py x pz planes).
-// Device plane i in [-gx, L+gx) maps to padded plane gp = x0 + i + e; planes outside [0, gnx+2e) are zero.
+// Host layout <-> device layout, staged through a small bounce buffer.  `stg` holds padded (or work-sized) host
+// planes [sp0, sp1) of the reference array, py x pz doubles each.  Device plane i in [-gx, L+gx) maps to host
+// plane gp = x0 + i + hoff (hoff = e for padded arrays, 0 for work-sized ones); planes outside [sp0, sp1) and
+// everything outside the lattice are written as zero.  One launch handles device planes [i0, i1).
 // WORKSIZED: host array has no ring (nx,ny,nz) — used for the pot_sub array.
 // ring_flag is set when a ring entry of the source is non-zero (CHECK).
 template <bool CHECK>
 __global__ void __launch_bounds__(256)
-    unpack_kernel(const double* __restrict__ host, double* __restrict__ dev, Geom g, long long hp0, long long hp1,
-                  int worksized, int* __restrict__ ring_flag) {
+    unpack_kernel(const double* __restrict__ stg, double* __restrict__ dev, Geom g, int i0, int i1, long long sp0,
+                  long long sp1, int worksized, int* __restrict__ ring_flag) {
     const int py = worksized ? g.ny : g.ny + 2 * g.e, pz = worksized ? g.nz : g.nz + 2 * g.e;
     const int hoff = worksized ? 0 : g.e;
-    const long long rows = (long long)(g.L + 2 * g.gx) * g.yp;
+    const long long rows = (long long)(i1 - i0) * g.yp;
     for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
-        const int i = (int)(r / g.yp) - g.gx, jr = (int)(r % g.yp);  // jr = j + e
-        const long long gp = g.x0 + i + hoff;                        // host plane index
-        const bool plane_ok = gp >= hp0 && gp < hp1;
+        const int i = i0 + (int)(r / g.yp), jr = (int)(r % g.yp);  // jr = j + e
+        const long long gp = g.x0 + i + hoff;                      // host plane index
+        const bool plane_ok = gp >= sp0 && gp < sp1;
         const bool x_inside = (g.x0 + i) >= 0 && (g.x0 + i) < g.gnx;
         const bool y_inside = jr >= g.e && jr < g.ny + g.e;
         const int hj = jr - g.e + hoff;
-        double* drow = dev + r * g.zp;
-        const double* hrow = host + ((gp - hp0) * py + hj) * (long long)pz;
+        double* drow = dev + ((long long)(i + g.gx) * g.yp + jr) * g.zp;
+        const double* hrow = stg + ((gp - sp0) * py + hj) * (long long)pz;
         for (int k = threadIdx.x; k < g.zp; k += blockDim.x) {
             double val = 0.0;
             if (plane_ok && x_inside && y_inside && k < g.nz) val = hrow[k + hoff];
@@ -411,26 +413,72 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-// device -> host layout for padded planes [hp0, hp1) (ring written as zeros)
+// device -> host layout for padded planes [sp0, sp1) into the bounce buffer (ring written as zeros)
 __global__ void __launch_bounds__(256)
-    pack_kernel(const double* __restrict__ dev, double* __restrict__ host, Geom g, long long hp0, long long hp1,
+    pack_kernel(const double* __restrict__ dev, double* __restrict__ stg, Geom g, long long sp0, long long sp1,
                 int worksized) {
     const int py = worksized ? g.ny : g.ny + 2 * g.e, pz = worksized ? g.nz : g.nz + 2 * g.e;
     const int hoff = worksized ? 0 : g.e;
-    const long long rows = (hp1 - hp0) * py;
+    const long long rows = (sp1 - sp0) * py;
     for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
-        const long long gp = hp0 + r / py;
+        const long long gp = sp0 + r / py;
         const int hj = (int)(r % py);
         const long long gi = gp - hoff;  // global work x
         const int j = hj - hoff;
         const bool inside = gi >= 0 && gi < g.gnx && j >= 0 && j < g.ny;
         const double* drow = inside ? dev + g.off((int)(gi - g.x0), j, 0) : nullptr;
-        double* hrow = host + r * pz;
+        double* hrow = stg + r * pz;
         for (int k = threadIdx.x; k < pz; k += blockDim.x) {
             const int kk = k - hoff;
             hrow[k] = (inside && kk >= 0 && kk < g.nz) ? drow[kk] : 0.0;
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Position-sensitive, order-independent checksum of the work-area sites of local planes [xb, xe): every site
+// contributes mix64(bits(psi) + golden * (global linear work index + 1)); the contributions are combined with
+// wrapping integer addition (out[0]) and xor (out[1]), both associative and commutative, so the result does not
+// depend on how the lattice is cut into slabs, tiles or threads.  Two slab-decomposed ranks and one single-GPU
+// context therefore agree on the checksum of the same planes iff the planes hold the same bits at the same sites.
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__global__ void __launch_bounds__(256)
+    checksum_kernel(const double* __restrict__ psi, Geom g, int xb, int xe, unsigned long long* __restrict__ out) {
+    unsigned long long s = 0, x = 0;
+    const long long rows = (long long)(xe - xb) * g.ny;
+    for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+        const int i = xb + (int)(r / g.ny), j = (int)(r % g.ny);
+        const double* row = psi + g.off(i, j, 0);
+        const unsigned long long base = ((unsigned long long)(g.x0 + i) * (unsigned long long)g.gny + (unsigned long long)j) * (unsigned long long)g.gnz;
+        for (int k = threadIdx.x; k < g.nz; k += blockDim.x) {
+            const unsigned long long h = mix64((unsigned long long)__double_as_longlong(row[k]) + 0x9E3779B97F4A7C15ull * (base + k + 1));
+            s += h;
+            x ^= h;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_down_sync(0xffffffffu, s, o);
+        x ^= __shfl_down_sync(0xffffffffu, x, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(out, s);      // integer atomics: exact and order independent
+        atomicXor(out + 1, x);
+    }
+}
+
+// busy-wait for `ns` nanoseconds (fault injection for the multi-GPU ordering tests: wafer_debug_halo_delay)
+__global__ void spin_kernel(unsigned long long ns) {
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+    do {
+        __nanosleep(1000);
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+    } while (t1 - t0 < ns);
 }
 
 }  // namespace wafer

@@ -48,7 +48,12 @@ struct wafer_ctx {
     int potsub_mode = 0;
     double potsub_scalar = 0.0;
     std::vector<double*> lowers;
-    double* staging = nullptr;  // host-layout bounce buffer for set/get (lazily allocated, never a field buffer)
+    // host <-> device: two small bounce buffers in the host layout, filled / drained on s_copy while the
+    // pack / unpack kernel of the other one runs on s_main (lazily allocated, never a field-sized buffer)
+    double* stg[2] = {nullptr, nullptr};
+    long long stg_planes = 0;       // padded host planes one bounce buffer holds
+    cudaStream_t s_copy = nullptr;
+    cudaEvent_t ev_stg_free[2] = {nullptr, nullptr}, ev_stg_full[2] = {nullptr, nullptr};
     double* partials = nullptr;
     long long partials_cap = 0;
     double* scal = nullptr;
@@ -65,6 +70,9 @@ struct wafer_ctx {
     int* p2p_timeout = nullptr;                           // device flag: a wait gave up (peer died)
     unsigned long long pass = 0;                          // boundary passes completed (same on every rank)
     int peer_L[2] = {0, 0};
+    int min_L = 0;                                        // smallest slab over all ranks: uniform overlap decision
+    unsigned long long dbg_halo_delay_ns = 0;             // fault injection: stall this rank's halo stream every pass
+    unsigned long long* d_cksum = nullptr;
     mutable std::string err;
     size_t bytes() const { return (size_t)g.total() * sizeof(double); }
 };
@@ -464,26 +472,52 @@ void owned_range(const wafer_ctx* ctx, long long* hp0, long long* hp1) {
     if (ctx->rank == ctx->world - 1) *hp1 = g.gnx + 2 * g.e;
 }
 
-// host_is_chunk: `host` already points at plane hp0 (the _slab entry points) instead of at the global array
+// Bounce buffers: 2 x ~128 MB regardless of the lattice size (a 1024^3 field is 8.8 GB, a full-size staging copy
+// of it was round 1's largest avoidable allocation).
 int ensure_staging(wafer_ctx* ctx) {
-    if (!ctx->staging) CK(cudaMalloc(&ctx->staging, ctx->bytes()));
+    if (ctx->stg[0]) return WAFER_OK;
+    const Geom& g = ctx->g;
+    const long long plane_h = (long long)(g.ny + 2 * g.e) * (g.nz + 2 * g.e);
+    const long long want = std::max<long long>(1, (128ll << 20) / (long long)(plane_h * sizeof(double)));
+    ctx->stg_planes = std::min<long long>(want, g.L + 2 * g.gx + 2 * g.e);
+    for (int b = 0; b < 2; ++b) {
+        CK(cudaMalloc(&ctx->stg[b], (size_t)(ctx->stg_planes * plane_h) * sizeof(double)));
+        CK(cudaEventCreateWithFlags(&ctx->ev_stg_free[b], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->ev_stg_full[b], cudaEventDisableTiming));
+    }
+    CK(cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking));
     return WAFER_OK;
 }
 
-int upload(wafer_ctx* ctx, const double* host, double* dst, bool worksized, bool check_ring, bool host_is_chunk = false) {
+// host -> device.  `host` points at plane `host_p0` of the reference array; planes [hp0, hp1) of it are read.
+// Device planes whose host plane lies outside [hp0, hp1) are zeroed (ghost planes a later halo exchange fills).
+int upload(wafer_ctx* ctx, const double* host, long long host_p0, long long hp0, long long hp1, double* dst, bool worksized,
+           bool check_ring) {
     const Geom& g = ctx->g;
-    long long hp0, hp1;
-    chunk_range(ctx, worksized, &hp0, &hp1);
     const long long py = worksized ? g.ny : g.ny + 2 * g.e, pz = worksized ? g.nz : g.nz + 2 * g.e;
+    const int hoff = worksized ? 0 : g.e;
     TRY(ensure_staging(ctx));
-    double* staging = ctx->staging;
-    CK(cudaMemcpyAsync(staging, host + (host_is_chunk ? 0 : hp0 * py * pz), (size_t)((hp1 - hp0) * py * pz) * sizeof(double),
-                       cudaMemcpyHostToDevice, ctx->s_main));
     if (check_ring) CK(cudaMemsetAsync(ctx->ring_flag, 0, sizeof(int), ctx->s_main));
-    const int grid = ctx->sm_count * 16;
-    if (check_ring) unpack_kernel<true><<<grid, 256, 0, ctx->s_main>>>(staging, dst, g, hp0, hp1, worksized ? 1 : 0, ctx->ring_flag);
-    else unpack_kernel<false><<<grid, 256, 0, ctx->s_main>>>(staging, dst, g, hp0, hp1, worksized ? 1 : 0, ctx->ring_flag);
-    TRY(post_launch(ctx));
+    CK(cudaEventRecord(ctx->ev_stg_free[0], ctx->s_main));  // everything queued so far precedes the first refill
+    CK(cudaEventRecord(ctx->ev_stg_free[1], ctx->s_main));
+    int k = 0;
+    for (int i0 = -g.gx; i0 < g.L + g.gx; i0 += (int)ctx->stg_planes, ++k) {
+        const int i1 = (int)std::min<long long>(i0 + ctx->stg_planes, g.L + g.gx), b = k & 1;
+        // host planes behind device planes [i0, i1), clipped to what the caller handed over
+        const long long sp0 = std::max<long long>(hp0, g.x0 + i0 + hoff), sp1 = std::min<long long>(hp1, g.x0 + i1 + hoff);
+        if (sp1 > sp0) {
+            CK(cudaStreamWaitEvent(ctx->s_copy, ctx->ev_stg_free[b], 0));
+            CK(cudaMemcpyAsync(ctx->stg[b], host + (sp0 - host_p0) * py * pz, (size_t)((sp1 - sp0) * py * pz) * sizeof(double),
+                               cudaMemcpyHostToDevice, ctx->s_copy));
+            CK(cudaEventRecord(ctx->ev_stg_full[b], ctx->s_copy));
+            CK(cudaStreamWaitEvent(ctx->s_main, ctx->ev_stg_full[b], 0));
+        }
+        const int grid = (int)std::min<long long>((long long)(i1 - i0) * g.yp, (long long)ctx->sm_count * 16);
+        if (check_ring) unpack_kernel<true><<<grid, 256, 0, ctx->s_main>>>(ctx->stg[b], dst, g, i0, i1, sp0, std::max(sp0, sp1), worksized ? 1 : 0, ctx->ring_flag);
+        else unpack_kernel<false><<<grid, 256, 0, ctx->s_main>>>(ctx->stg[b], dst, g, i0, i1, sp0, std::max(sp0, sp1), worksized ? 1 : 0, ctx->ring_flag);
+        TRY(post_launch(ctx));
+        CK(cudaEventRecord(ctx->ev_stg_free[b], ctx->s_main));
+    }
     if (check_ring) {
         int flag = 0;
         CK(cudaMemcpyAsync(&flag, ctx->ring_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->s_main));
@@ -498,19 +532,42 @@ int upload(wafer_ctx* ctx, const double* host, double* dst, bool worksized, bool
     return WAFER_OK;
 }
 
-int download(wafer_ctx* ctx, const double* src, double* host, bool host_is_chunk = false) {
+// device -> host: padded planes [hp0, hp1) of the global array into `host`, which points at plane host_p0
+int download(wafer_ctx* ctx, const double* src, double* host, long long host_p0, long long hp0, long long hp1) {
     const Geom& g = ctx->g;
-    long long hp0, hp1;
-    owned_range(ctx, &hp0, &hp1);
     const long long py = g.ny + 2 * g.e, pz = g.nz + 2 * g.e;
     TRY(ensure_staging(ctx));
-    double* staging = ctx->staging;
-    pack_kernel<<<ctx->sm_count * 16, 256, 0, ctx->s_main>>>(src, staging, g, hp0, hp1, 0);
-    TRY(post_launch(ctx));
-    CK(cudaMemcpyAsync(host + (host_is_chunk ? 0 : hp0 * py * pz), staging, (size_t)((hp1 - hp0) * py * pz) * sizeof(double),
-                       cudaMemcpyDeviceToHost, ctx->s_main));
+    CK(cudaEventRecord(ctx->ev_stg_free[0], ctx->s_main));
+    CK(cudaEventRecord(ctx->ev_stg_free[1], ctx->s_main));
+    int k = 0;
+    for (long long sp0 = hp0; sp0 < hp1; sp0 += ctx->stg_planes, ++k) {
+        const long long sp1 = std::min(hp1, sp0 + ctx->stg_planes);
+        const int b = k & 1;
+        CK(cudaStreamWaitEvent(ctx->s_main, ctx->ev_stg_free[b], 0));
+        const int grid = (int)std::min<long long>((sp1 - sp0) * py, (long long)ctx->sm_count * 16);
+        pack_kernel<<<grid, 256, 0, ctx->s_main>>>(src, ctx->stg[b], g, sp0, sp1, 0);
+        TRY(post_launch(ctx));
+        CK(cudaEventRecord(ctx->ev_stg_full[b], ctx->s_main));
+        CK(cudaStreamWaitEvent(ctx->s_copy, ctx->ev_stg_full[b], 0));
+        CK(cudaMemcpyAsync(host + (sp0 - host_p0) * py * pz, ctx->stg[b], (size_t)((sp1 - sp0) * py * pz) * sizeof(double),
+                           cudaMemcpyDeviceToHost, ctx->s_copy));
+        CK(cudaEventRecord(ctx->ev_stg_free[b], ctx->s_copy));
+    }
+    CK(cudaStreamSynchronize(ctx->s_copy));
     CK(cudaStreamSynchronize(ctx->s_main));
     return WAFER_OK;
+}
+
+// global-array entry points: this rank's chunk (owned + ghost planes) in, its owned planes out
+int upload_global(wafer_ctx* ctx, const double* host, double* dst, bool worksized, bool check_ring) {
+    long long hp0, hp1;
+    chunk_range(ctx, worksized, &hp0, &hp1);
+    return upload(ctx, host, 0, hp0, hp1, dst, worksized, check_ring);
+}
+int download_global(wafer_ctx* ctx, const double* src, double* host) {
+    long long hp0, hp1;
+    owned_range(ctx, &hp0, &hp1);
+    return download(ctx, src, host, 0, hp0, hp1);
 }
 
 int alloc_field(wafer_ctx* ctx, double** p) {
@@ -575,7 +632,8 @@ int create_impl(const wafer_params* params, wafer_ctx* ctx) {
     g.zp = (int)(((long long)g.nz + 2 * g.e + 15) / 16 * 16);
     g.plane = (long long)g.yp * g.zp;
     g.gnx = p.nx; g.gny = p.ny; g.gnz = p.nz;
-    REQUIRE(ctx->world == 1 || g.L >= g.gx, "every rank needs at least `ext` planes of the lattice");
+    ctx->min_L = (int)(p.nx / (uint64_t)ctx->world);  // wafer_slab_partition: the last ranks own floor(nx/world) planes
+    REQUIRE(ctx->world == 1 || ctx->min_L >= g.gx, "every rank needs at least as many planes as the ghost depth (2 for ThreePoint, else ext)");
 
     int lo, hi;
     CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -647,7 +705,14 @@ int wafer_destroy(wafer_ctx* ctx) {
     cudaFree(ctx->flags); cudaFree(ctx->p2p_timeout);
     for (double* q : ctx->lowers) cudaFree(q);
     cudaFree(ctx->psi[0]); cudaFree(ctx->psi[1]); cudaFree(ctx->v); cudaFree(ctx->a); cudaFree(ctx->b);
-    cudaFree(ctx->staging); cudaFree(ctx->potsub_arr); cudaFree(ctx->partials); cudaFree(ctx->scal); cudaFree(ctx->ring_flag);
+    for (int b = 0; b < 2; ++b) {
+        cudaFree(ctx->stg[b]);
+        if (ctx->ev_stg_free[b]) cudaEventDestroy(ctx->ev_stg_free[b]);
+        if (ctx->ev_stg_full[b]) cudaEventDestroy(ctx->ev_stg_full[b]);
+    }
+    if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
+    cudaFree(ctx->d_cksum);
+    cudaFree(ctx->potsub_arr); cudaFree(ctx->partials); cudaFree(ctx->scal); cudaFree(ctx->ring_flag);
     if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
     if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
     if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
@@ -691,7 +756,7 @@ int wafer_set_potential(wafer_ctx* ctx, const double* v_padded) {
     if (!ctx) return WAFER_ERR_INVALID;
     REQUIRE(v_padded, "v_padded is NULL");
     CK(cudaSetDevice(ctx->dev));
-    TRY(upload(ctx, v_padded, ctx->v, false, false));
+    TRY(upload_global(ctx, v_padded, ctx->v, false, false));
     TRY(ensure_ab(ctx));
     ctx->have_v = true;
     return WAFER_OK;
@@ -702,7 +767,7 @@ int wafer_get_potential(wafer_ctx* ctx, double* v_padded) {
     REQUIRE(v_padded, "v_padded is NULL");
     if (!ctx->have_v) { ctx->err = "potential not set"; return WAFER_ERR_NOT_READY; }
     CK(cudaSetDevice(ctx->dev));
-    return download(ctx, ctx->v, v_padded);
+    return download_global(ctx, ctx->v, v_padded);
 }
 
 int wafer_set_pot_sub_scalar(wafer_ctx* ctx, double c) {
@@ -718,7 +783,7 @@ int wafer_set_pot_sub_array(wafer_ctx* ctx, const double* work) {
     REQUIRE(work, "pot_sub array is NULL");
     CK(cudaSetDevice(ctx->dev));
     if (!ctx->potsub_arr) TRY(alloc_field(ctx, &ctx->potsub_arr));
-    TRY(upload(ctx, work, ctx->potsub_arr, true, false));
+    TRY(upload_global(ctx, work, ctx->potsub_arr, true, false));
     ctx->potsub_mode = 2;
     return WAFER_OK;
 }
@@ -727,7 +792,7 @@ int wafer_set_phi(wafer_ctx* ctx, const double* phi_padded) {
     if (!ctx) return WAFER_ERR_INVALID;
     REQUIRE(phi_padded, "phi_padded is NULL");
     CK(cudaSetDevice(ctx->dev));
-    const int rc = upload(ctx, phi_padded, ctx->psi[ctx->cur], false, true);
+    const int rc = upload_global(ctx, phi_padded, ctx->psi[ctx->cur], false, true);
     ctx->have_phi = rc == WAFER_OK;
     return rc;
 }
@@ -737,7 +802,7 @@ int wafer_get_phi(wafer_ctx* ctx, double* phi_padded) {
     REQUIRE(phi_padded, "phi_padded is NULL");
     if (!ctx->have_phi) { ctx->err = "phi not set"; return WAFER_ERR_NOT_READY; }
     CK(cudaSetDevice(ctx->dev));
-    return download(ctx, ctx->psi[ctx->cur], phi_padded);
+    return download_global(ctx, ctx->psi[ctx->cur], phi_padded);
 }
 
 int wafer_slab_planes(const wafer_ctx* ctx, int32_t which, uint64_t* p0, uint64_t* p1) {
@@ -754,9 +819,23 @@ int wafer_set_phi_slab(wafer_ctx* ctx, const double* chunk) {
     if (!ctx) return WAFER_ERR_INVALID;
     REQUIRE(chunk, "chunk is NULL");
     CK(cudaSetDevice(ctx->dev));
-    const int rc = upload(ctx, chunk, ctx->psi[ctx->cur], false, true, true);
+    long long hp0, hp1;
+    chunk_range(ctx, false, &hp0, &hp1);
+    const int rc = upload(ctx, chunk, hp0, hp0, hp1, ctx->psi[ctx->cur], false, true);
     ctx->have_phi = rc == WAFER_OK;
     return rc;
+}
+
+int wafer_set_phi_owned(wafer_ctx* ctx, const double* chunk) {
+    if (!ctx) return WAFER_ERR_INVALID;
+    REQUIRE(chunk, "chunk is NULL");
+    CK(cudaSetDevice(ctx->dev));
+    long long hp0, hp1;
+    owned_range(ctx, &hp0, &hp1);
+    const int rc = upload(ctx, chunk, hp0, hp0, hp1, ctx->psi[ctx->cur], false, true);
+    ctx->have_phi = rc == WAFER_OK;
+    if (rc != WAFER_OK) return rc;
+    return exchange(ctx, ctx->psi[ctx->cur], ctx->s_main);  // ghost planes come from the neighbours (collective)
 }
 
 int wafer_get_phi_slab(wafer_ctx* ctx, double* chunk) {
@@ -764,7 +843,9 @@ int wafer_get_phi_slab(wafer_ctx* ctx, double* chunk) {
     REQUIRE(chunk, "chunk is NULL");
     if (!ctx->have_phi) { ctx->err = "phi not set"; return WAFER_ERR_NOT_READY; }
     CK(cudaSetDevice(ctx->dev));
-    return download(ctx, ctx->psi[ctx->cur], chunk, true);
+    long long hp0, hp1;
+    owned_range(ctx, &hp0, &hp1);
+    return download(ctx, ctx->psi[ctx->cur], chunk, hp0, hp0, hp1);
 }
 
 int wafer_push_lower(wafer_ctx* ctx, const double* q_padded) {
@@ -774,7 +855,7 @@ int wafer_push_lower(wafer_ctx* ctx, const double* q_padded) {
     CK(cudaSetDevice(ctx->dev));
     double* q = nullptr;
     TRY(alloc_field(ctx, &q));
-    const int rc = upload(ctx, q_padded, q, false, true);
+    const int rc = upload_global(ctx, q_padded, q, false, true);
     if (rc != WAFER_OK) { cudaFree(q); return rc; }
     ctx->lowers.push_back(q);
     return WAFER_OK;
@@ -796,7 +877,7 @@ int wafer_get_lower(wafer_ctx* ctx, uint32_t idx, double* q_padded) {
     if (!ctx) return WAFER_ERR_INVALID;
     REQUIRE(q_padded && idx < ctx->lowers.size(), "no such lower state");
     CK(cudaSetDevice(ctx->dev));
-    return download(ctx, ctx->lowers[idx], q_padded);
+    return download_global(ctx, ctx->lowers[idx], q_padded);
 }
 
 int wafer_phi_from_lower(wafer_ctx* ctx, uint32_t idx) {
@@ -915,7 +996,9 @@ int wafer_evolve(wafer_ctx* ctx, uint8_t wnum_in, uint64_t steps) {
     const Geom& g = ctx->g;
     const int wnum = std::min<int>(wnum_in, (int)ctx->lowers.size());
     const bool excited = wnum_in > 0;  // grid.rs:674: norm/normalise run for wnum > 0 even with an empty w_store
-    const bool overlap = ctx->world > 1 && !excited && g.L > 2 * g.gx;
+    // every rank must take the same branch (one side calling NCCL while the other stores through peer memory would
+    // hang): decide from the smallest slab of the decomposition, not from this rank's own L
+    const bool overlap = ctx->world > 1 && !excited && ctx->min_L > 2 * g.gx;
     if (overlap) {
         CK(cudaEventRecord(ctx->ev_main, ctx->s_main));
         CK(cudaEventRecord(ctx->ev_halo, ctx->s_main));
@@ -936,6 +1019,10 @@ int wafer_evolve(wafer_ctx* ctx, uint8_t wnum_in, uint64_t steps) {
             // boundary planes + halo on the high-priority stream, interior on the main stream
             CK(cudaStreamWaitEvent(ctx->s_halo, ctx->ev_main, 0));
             CK(cudaStreamWaitEvent(ctx->s_main, ctx->ev_halo, 0));
+            if (ctx->dbg_halo_delay_ns) {
+                spin_kernel<<<1, 1, 0, ctx->s_halo>>>(ctx->dbg_halo_delay_ns);
+                TRY(post_launch(ctx));
+            }
             if (fused) {
                 // my ghost planes of `cur` hold the neighbours' pass-(n-1) boundary planes once their flag says so;
                 // the same flag says they are done reading the ghost planes (of their `nxt`) that I overwrite now
@@ -980,7 +1067,19 @@ int wafer_evolve(wafer_ctx* ctx, uint8_t wnum_in, uint64_t steps) {
         }
         done += two ? 2 : 1;
     }
-    if (overlap) CK(cudaStreamWaitEvent(ctx->s_main, ctx->ev_halo, 0));
+    if (overlap) {
+        static const bool skip_final_wait = getenv("WAFER_DEBUG_SKIP_FINAL_WAIT") && atoi(getenv("WAFER_DEBUG_SKIP_FINAL_WAIT")) == 1;
+        if (fused && !skip_final_wait) {  // the env knob exists only so that the drift test can prove it catches the race
+            // The neighbours' boundary stores of the LAST pass must have landed in my ghost planes before anything
+            // that follows on the main stream reads them (observables, Gram-Schmidt, downloads, w_store.push) or
+            // overwrites them (normalise, uploads): wait for their pass counter to reach mine.  Without this a rank
+            // that runs ahead returns with ghost planes that are one same-buffer pass (4 steps) old.
+            p2p_wait_kernel<<<1, 1, 0, ctx->s_halo>>>(ctx->flags, ctx->pass, has_lo, has_hi, ctx->p2p_timeout);
+            TRY(post_launch(ctx));
+            CK(cudaEventRecord(ctx->ev_halo, ctx->s_halo));
+        }
+        CK(cudaStreamWaitEvent(ctx->s_main, ctx->ev_halo, 0));
+    }
     return WAFER_OK;
 }
 
@@ -1149,6 +1248,35 @@ int wafer_selftest_division(wafer_ctx* ctx, double den, uint64_t n, uint64_t see
     CK(cudaStreamSynchronize(ctx->s_main));
     cudaFree(d);
     *mismatches = h;
+    return WAFER_OK;
+}
+
+int wafer_phi_checksum(wafer_ctx* ctx, uint64_t x_begin, uint64_t x_end, uint64_t out[2]) {
+    if (!ctx) return WAFER_ERR_INVALID;
+    REQUIRE(out, "out is NULL");
+    TRY(ready(ctx, false));
+    CK(cudaSetDevice(ctx->dev));
+    const Geom& g = ctx->g;
+    if (!ctx->d_cksum) CK(cudaMalloc(&ctx->d_cksum, 2 * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(ctx->d_cksum, 0, 2 * sizeof(unsigned long long), ctx->s_main));
+    const long long xb = std::max<long long>((long long)x_begin, g.x0) - g.x0;
+    const long long xe = std::min<long long>((long long)std::min<uint64_t>(x_end, (uint64_t)g.gnx), g.x0 + g.L) - g.x0;
+    if (xe > xb) {
+        const int grid = (int)std::min<long long>((xe - xb) * g.ny, (long long)ctx->sm_count * 16);
+        checksum_kernel<<<grid, 256, 0, ctx->s_main>>>(ctx->psi[ctx->cur], g, (int)xb, (int)xe, ctx->d_cksum);
+        TRY(post_launch(ctx));
+    }
+    unsigned long long h[2] = {0, 0};
+    CK(cudaMemcpyAsync(h, ctx->d_cksum, sizeof(h), cudaMemcpyDeviceToHost, ctx->s_main));
+    CK(cudaStreamSynchronize(ctx->s_main));
+    out[0] = h[0]; out[1] = h[1];
+    return check_p2p_timeout(ctx);
+}
+
+int wafer_debug_halo_delay(wafer_ctx* ctx, uint64_t nanoseconds) {
+    if (!ctx) return WAFER_ERR_INVALID;
+    REQUIRE(nanoseconds <= 1000000000ull, "delay is capped at one second per pass");
+    ctx->dbg_halo_delay_ns = nanoseconds;
     return WAFER_OK;
 }
 
