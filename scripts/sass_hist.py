@@ -45,12 +45,29 @@ def classify(op):
     return "other"
 
 
+def drop_cold_blocks(sel):
+    """remove forward-branched-over regions that only marshal arguments for out-of-line CALLs (the cold division
+    paths): they contain CALL but no f64 arithmetic of their own"""
+    addr = {a: i for i, (a, t) in enumerate(sel)}
+    skip = set()
+    for i, (a, t) in enumerate(sel):
+        m = re.search(r"BRA(?:\.\S+)*\s+(?:!?U?P\d+,\s*)?(0x[0-9a-f]+)", t)
+        if m:
+            tg = int(m.group(1), 16)
+            if tg > a and tg in addr:
+                body = [x[1] for x in sel[i + 1:addr[tg]]]
+                if any("CALL" in x for x in body) and not any(re.search(r"\b(DADD|DMUL|DFMA)\b", x) for x in body):
+                    skip.update(range(i + 1, addr[tg]))
+    return [x for i, x in enumerate(sel) if i not in skip]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("lib")
     ap.add_argument("kernel")
     ap.add_argument("--range", nargs=2, default=None)
     ap.add_argument("--loops", action="store_true", help="list backward branches (loop candidates)")
+    ap.add_argument("--hot", action="store_true", help="leave out the cold out-of-line-call blocks inside the range")
     a = ap.parse_args()
     for name, ins in disasm(a.lib, a.kernel).items():
         print("== %s: %d instructions" % (name, len(ins)))
@@ -60,7 +77,10 @@ def main():
                 if m and int(m.group(1), 16) < addr:
                     print("   loop %#x..%#x  (%d instr)  %s" % (int(m.group(1), 16), addr, (addr - int(m.group(1), 16)) // 16 + 1, t))
         lo, hi = (int(a.range[0], 16), int(a.range[1], 16)) if a.range else (0, 1 << 60)
-        sel = [t for addr, t in ins if lo <= addr <= hi]
+        sel = [(addr, t) for addr, t in ins if lo <= addr <= hi]
+        if a.hot:
+            sel = drop_cold_blocks(sel)
+        sel = [t for _, t in sel]
         ops = collections.Counter(opcode(t) for t in sel)
         cls = collections.Counter()
         for op, n in ops.items():

@@ -3,7 +3,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libwafer_b200.so")
+# WAFER_B200_LIB: another build of the same library (kernel-variant A/B runs, scripts/gpu_libs.sh); never a fallback
+LIB_PATH = os.environ.get("WAFER_B200_LIB") or os.path.join(_HERE, "libwafer_b200.so")
 
 _dp = C.POINTER(C.c_double)
 

@@ -83,6 +83,7 @@ __device__ __forceinline__ void iteration(Smem<E>& sm, double2 (&q)[2][Cfg<E>::N
         const double* vs = sm.st[s_new].v + ln.cb;  // V plane c rides with psi plane c+E
         constexpr int IC = qslot<E>(PHASE, E);
         const bool nofast = !dc.fast;
+        const double hdt = D_MUL(dt, 0.5);
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
             const double* row = psc + (s + E) * BW;
@@ -114,8 +115,8 @@ __device__ __forceinline__ void iteration(Smem<E>& sm, double2 (&q)[2][Cfg<E>::N
             const double2 vv = *reinterpret_cast<const double2*>(vs + s * BW);
             unsigned b0 = 0u, b1 = 0u;
             double a0, bd0, a1, bd1;
-            tb::ab_fast(vv.x, dt, a0, bd0, b0);
-            tb::ab_fast(vv.y, dt, a1, bd1, b1);
+            tb::ab_fast(vv.x, hdt, dt, a0, bd0, b0);
+            tb::ab_fast(vv.y, hdt, dt, a1, bd1, b1);
             double2 r;
             r.x = tb::update_fast(w.x, a0, bd0, s0, dc, b0);
             r.y = tb::update_fast(w.y, a1, bd1, s1, dc, b1);
