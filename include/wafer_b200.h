@@ -46,7 +46,8 @@ typedef enum {
 /* flags */
 #define WAFER_FLAG_AB_ARRAYS 0x1u   /* keep A and B as arrays (32 B/update) instead of recomputing them from V in the sweep */
 #define WAFER_FLAG_TMA_ONE_STEP 0x8u /* one-step sweeps (5/7-point, excited states, odd tail) through the TMA-pipelined kernel;
-                                        already the default when world == 1 and WAFER_FLAG_SIMPLE_SWEEP is not set */
+                                        already the default unless WAFER_FLAG_SIMPLE_SWEEP or WAFER_FLAG_AB_ARRAYS is set */
+#define WAFER_FLAG_NO_FUSED_CHECK 0x10u /* do not fold the check's point-wise sums into the last sweep of wafer_evolve      */
 #define WAFER_FLAG_SIMPLE_SWEEP 0x4u /* force the plain register-queue sweep (no TMA pipeline, one step per pass)          */
 
 typedef struct {

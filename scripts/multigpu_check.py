@@ -100,7 +100,7 @@ def main():
     if use_p2p:
         connect(multi)
     if rank == 1 % world:
-        multi.debug_halo_delay(int(os.environ.get("WAFER_DRIFT_DELAY_NS", 40000)))
+        multi.debug_halo_delay(int(os.environ.get("WAFER_DRIFT_DELAY_NS", 300000)))
     x0, x1 = multi.slab
     drift = dict(bitwise=[], obs_rel=[])
     for lat in (single, multi):
@@ -114,8 +114,10 @@ def main():
                 # the stateless drop-in round trip: owned planes out to the host and back in, ghosts re-fetched
                 lat.set_phi_owned(lat.get_phi_slab()) if lat is multi else lat.set_phi(lat.get_phi())
             lat.evolve(0, sweeps + rnd)  # rnd = 1: odd count -> the one-step tail pass takes part too
-            ck = lat.phi_checksum(x0, x1)
+            # the observables kernel is queued straight behind the last sweep, with no host synchronisation in between:
+            # it reads the ghost planes the (stalled) neighbour is still about to store
             obs = lat.compute_observables()
+            ck = lat.phi_checksum(x0, x1)
             per.append((ck, obs))
         (cs, os_), (cm, om) = per
         drift["bitwise"].append(cs == cm)

@@ -434,6 +434,74 @@ def test_evolve_excited_state_steps(wb, oracle, ext, nlow):
         assert abs((q * got).sum()) < 1e-13
 
 
+@pytest.mark.parametrize("nlow", [5, 6])
+def test_evolve_excited_more_states_than_one_pass_takes(wb, oracle, nlow):
+    """more stored states than the sweep fuses (4) / than one projection pass handles (4): the remaining overlaps come
+    from extra dot passes; the stored states are deliberately NOT orthogonal, so the Gram-matrix solve of the
+    modified-Gram-Schmidt coefficients (kernels.cuh gs_coeff_kernel) is exercised for real"""
+    rng = np.random.default_rng(41)
+    shape, ext = (14, 18, 20), 1
+    g = oracle.make_grid(*shape, ext=ext, dn=0.1, dt=2e-3, mass=1.0)
+    v = oracle.potential(g, "Harmonic")
+    a, b = oracle.build_ab(v, g.dt)
+    lowers = []
+    for _ in range(nlow):
+        q = np.zeros(g.padded_shape)
+        npr.work(q, ext)[...] = rng.normal(size=shape)
+        lowers.append(np.ascontiguousarray(q / np.sqrt((q * q).sum())))
+    phi = np.zeros(g.padded_shape)
+    npr.work(phi, ext)[...] = rng.normal(size=shape)
+    oracle.set_sum_mode(1)
+    try:
+        with wb.Lattice(shape, CD[ext], dn=g.dn, dt=g.dt, mass=g.mass) as lat:
+            lat.set_potential(v)
+            for q in lowers:
+                lat.push_lower(q)
+            lat.set_phi(phi)
+            lat.evolve(nlow, 3)
+            got = lat.get_phi()
+            lat.set_phi(phi)
+            lat.orthogonalise_wavefunction(nlow)
+            got_o = lat.get_phi()
+        ref_o = phi.copy()
+        oracle.orthogonalise(ref_o, lowers)
+        oracle.evolve(g, phi, a, b, 3, lowers=lowers)
+    finally:
+        oracle.set_sum_mode(0)
+    assert _l2(got_o, ref_o) < 1e-12
+    assert _l2(got, phi) < 1e-11
+
+
+@pytest.mark.parametrize("ext,potsub", [(1, None), (1, 2.5), (2, "array"), (3, 1.0)])
+def test_check_sums_fused_into_the_last_sweep(wb, oracle, ext, potsub):
+    """evolve() of >= 64 ground-state steps ends with a sweep that also leaves sum psi^2, sum psi^2 pot_sub and
+    sum psi^2 r2 (north-star: reductions fused into the final sweep before each check); the check that follows adds only
+    the energy pass.  Same numbers as the un-fused path and as the oracle (grid.rs:303-445)."""
+    shape = (22, 35, 61)
+    g, v, phi = _rand_state(oracle, shape, ext, 43, dn=0.1, mass=1.0)
+    v *= 0.1
+    a, b = oracle.build_ab(v, g.dt)
+    ps = np.random.default_rng(3).normal(size=shape) if potsub == "array" else potsub
+    outs = []
+    for flags in (0, 0x10):  # 0x10 = WAFER_FLAG_NO_FUSED_CHECK
+        with wb.Lattice(shape, CD[ext], dn=g.dn, dt=g.dt, mass=g.mass, flags=flags) as lat:
+            lat.set_potential(v)
+            lat.set_pot_sub(ps)
+            lat.set_phi(phi)
+            n0 = lat.kernel_launches
+            lat.evolve(0, 70)
+            psi = lat.get_phi()
+            outs.append((lat.check(0), psi, lat.kernel_launches - n0))
+    ref = phi.copy()
+    oracle.evolve(g, ref, a, b, 70)
+    assert np.array_equal(outs[0][1], ref) and np.array_equal(outs[1][1], ref)
+    want = oracle.observables(g, ref, v, ps)
+    scale = max(abs(want["energy"]), want["norm2"], abs(want["r2"]))
+    for got, _, _ in outs:
+        for key in want:
+            assert abs(got[key] - want[key]) <= SUM_TOL * scale, (key, got[key], want[key])
+
+
 def test_check_fuses_observables_normalise_orthogonalise(wb, oracle):
     """grid.rs:127-135"""
     g, v, phi = _rand_state(oracle, (16, 16, 16), 1, 23, dn=0.1, mass=1.0)

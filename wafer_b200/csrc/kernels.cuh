@@ -310,41 +310,93 @@ __global__ void __launch_bounds__(SW_BX* SW_BY)
 // All work on double2 (buffers are 128-byte aligned and a multiple of 16 doubles long).
 constexpr int EW_THREADS = 256;
 
-// psi = psi / sqrt(norm2)                                                         (grid.rs:465-468)
-// psi -= q_prev * s_prev  (optional, first)                                       (grid.rs:488-490)
-// partial sum of q_next * psi over owned planes (optional)                        (grid.rs:482-487)
-// norm2 / s_prev are read from device memory so that no host round trip sits between passes.
-template <bool NORMALISE, bool AXPY, bool DOT>
+// ---------------------------------------------------------------------------------------------------------
+// Gram-Schmidt in two passes instead of 2k (grid.rs:477-492 is k sequential "dot, then axpy" sweeps):
+//   pass 1  dots_kernel<K>      raw_i = sum q_i * psi over the owned planes, all K stored states at once (or fused
+//                               into the sweep, sweep_tma1.cuh NRED)
+//   scalars gs_coeff_kernel     s_0 = d_0,  s_i = d_i - sum_{j<i} G_ij s_j   with d_i = raw_i / sqrt(norm2) and the
+//                               Gram matrix G_ij = <q_i, q_j> of the stored states (measured when a state is pushed)
+//   pass 2  project_kernel<K>   psi = ((psi / sqrt(norm2)) - q_0 s_0) - q_1 s_1 ...   element-wise in the reference's order
+// In exact arithmetic s_i IS the modified-Gram-Schmidt overlap <q_i, psi - sum_{j<i} q_j s_j> of the reference, for
+// arbitrary (also non-orthogonal) stored states; in floating point it differs from it like two summation orders do.
+constexpr int GS_GROUP = 4;  // stored states handled per pass
+struct LowerPtrs {
+    const double* q[GS_GROUP];
+};
+
+template <int K>
 __global__ void __launch_bounds__(EW_THREADS)
-    gs_pass_kernel(double* __restrict__ psi, long long n2, const double* __restrict__ norm2_ptr,
-                   const double* __restrict__ q_prev, const double* __restrict__ s_prev_ptr,
-                   const double* __restrict__ q_next, long long own_b2, long long own_e2,
-                   double* __restrict__ partials) {
-    double norm = 1.0, sp = 0.0;
+    dots_kernel(const double* __restrict__ psi, LowerPtrs lw, long long own_b2, long long own_e2, double* __restrict__ partials) {
+    double acc[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] = 0.0;
+    const double2* p2 = reinterpret_cast<const double2*>(psi);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = own_b2 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < own_e2; i += stride) {
+        const double2 w = p2[i];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const double2 q = __ldg(reinterpret_cast<const double2*>(lw.q[k]) + i);
+            acc[k] = D_ADD(acc[k], D_ADD(D_MUL(q.x, w.x), D_MUL(q.y, w.y)));
+        }
+    }
+    block_reduce_store<K>(acc, partials, gridDim.x, blockIdx.x);
+}
+
+// psi = psi / sqrt(*norm2_ptr) (NORMALISE, grid.rs:465-468: a true division), then psi -= q_k * coef[k] for k = 0..K-1 in
+// order (grid.rs:488-490), over the whole slab buffer (ghost planes included: every rank applies the same scalars, so
+// neighbouring ranks keep bit-identical ghost copies without a halo exchange)
+template <int K, bool NORMALISE>
+__global__ void __launch_bounds__(EW_THREADS)
+    project_kernel(double* __restrict__ psi, long long n2, const double* __restrict__ norm2_ptr, LowerPtrs lw,
+                   const double* __restrict__ coef) {
+    double norm = 1.0, s[K > 0 ? K : 1];
     if (NORMALISE) norm = __dsqrt_rn(*norm2_ptr);
-    if (AXPY) sp = *s_prev_ptr;
-    double acc[1] = {0.0};
+#pragma unroll
+    for (int k = 0; k < K; ++k) s[k] = coef[k];
     double2* p2 = reinterpret_cast<double2*>(psi);
-    const double2* qp2 = reinterpret_cast<const double2*>(q_prev);
-    const double2* qn2 = reinterpret_cast<const double2*>(q_next);
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
         double2 w = p2[i];
         if (NORMALISE) { w.x = D_DIV(w.x, norm); w.y = D_DIV(w.y, norm); }
-        if (AXPY) {
-            const double2 q = qp2[i];
-            w.x = D_SUB(w.x, D_MUL(q.x, sp));
-            w.y = D_SUB(w.y, D_MUL(q.y, sp));
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const double2 q = __ldg(reinterpret_cast<const double2*>(lw.q[k]) + i);
+            w.x = D_SUB(w.x, D_MUL(q.x, s[k]));
+            w.y = D_SUB(w.y, D_MUL(q.y, s[k]));
         }
-        if (NORMALISE || AXPY) p2[i] = w;
-        if (DOT) {
-            if (i >= own_b2 && i < own_e2) {
-                const double2 q = qn2[i];
-                acc[0] = D_ADD(acc[0], D_ADD(D_MUL(q.x, w.x), D_MUL(q.y, w.y)));
-            }
+        p2[i] = w;
+    }
+}
+
+// One CTA: (REDUCE) fixed-order sums of `nrows` rows of per-CTA partials -> raw[0..nrows); (COEF) the Gram-Schmidt
+// coefficients from raw.  Split in two launches only when an all-reduce over ranks sits between them.
+//   raw layout: raw[dot0 + i] = sum q_i psi for i < k; norm2_ptr (may be raw[0] or the observables' norm2 or NULL)
+template <bool REDUCE, bool COEF>
+__global__ void __launch_bounds__(1024)
+    gs_coeff_kernel(const double* __restrict__ partials, int nblocks, int nrows, double* __restrict__ raw, int k,
+                    const double* __restrict__ dots, const double* __restrict__ norm2_ptr, const double* __restrict__ gram,
+                    int gram_ld, double* __restrict__ coef) {
+    if (REDUCE) {
+        __shared__ double fin[1];
+        for (int r = 0; r < nrows; ++r) {
+            double v[1] = {0.0};
+            for (int i = threadIdx.x; i < nblocks; i += blockDim.x) v[0] = D_ADD(v[0], partials[(long long)r * nblocks + i]);
+            __syncthreads();  // the reduction scratch of the previous row is free again
+            block_reduce_store<1>(v, fin, 1, 0);
+            __syncthreads();
+            if (threadIdx.x == 0) raw[r] = fin[0];
+        }
+        __syncthreads();
+    }
+    if (COEF && threadIdx.x == 0) {
+        const double norm = norm2_ptr ? __dsqrt_rn(*norm2_ptr) : 1.0;
+        for (int i = 0; i < k; ++i) {
+            double s = norm2_ptr ? D_DIV(dots[i], norm) : dots[i];
+            for (int j = 0; j < i; ++j) s = D_SUB(s, D_MUL(gram[(long long)i * gram_ld + j], coef[j]));
+            coef[i] = s;
         }
     }
-    if (DOT) block_reduce_store<1>(acc, partials, gridDim.x, blockIdx.x);
 }
 
 // sum of psi^2 over the owned planes (pads and ghost rows are zero, so this equals the work-area norm2)

@@ -59,17 +59,52 @@ __host__ __device__ constexpr int qslot(int phase, int j) {
 struct Lane1 {
     int cb;            // element offset of the lane's column pair in row 2*warp of a 64-wide region
     bool st0, st1;     // store column 0 / column 1 of the pair (inside the tile's output columns and the lattice)
+    double yy2[2], zz2[2];  // (j - cy)^2 of the two rows, (k - cz)^2 of the two columns (potential.rs:366-371), check modes
 };
 struct Tile1 {
     bool yin[2];       // slot row inside the lattice
     int xa, xz;        // output planes [xa, xz)
 };
 
-template <int E, bool NORM, int PHASE>
+// MODE of the kernel:
+//   0..5         sweep with NRED = MODE running sums: 1 = sum psi'^2 (grid.rs:675-678), 1 + k = additionally the overlaps
+//                sum q_i psi' with k <= MAX_FUSED_LOWERS stored states (grid.rs:482-487), read once at the output sites
+//   MODE_OBS+p   compute_observables (grid.rs:303-445) of the INPUT field, nothing stored: four sums
+//                [0] ((v w) w) - ((w S)/den), [1] w w, [2] (w w) potsub, [3] (w w) r2;  p = 0 none, 1 scalar, 2 array,
+//                p = 3: sum [0] only
+//   MODE_CHK+p   sweep that also leaves the three point-wise sums of the check that follows it, taken on psi':
+//                [0] w w, [1] (w w) potsub, [2] (w w) r2  (north-star: "block reductions fused into the final sweep
+//                before each check"; the energy needs neighbours of psi' and stays a pass of its own)
+constexpr int MAX_FUSED_LOWERS = 4;
+constexpr int MODE_OBS = 8, MODE_CHK = 16;
+template <int MODE>
+struct Mode {
+    static constexpr bool obs = MODE >= MODE_OBS && MODE < MODE_CHK;
+    static constexpr bool chk = MODE >= MODE_CHK;
+    static constexpr int potsub = obs ? MODE - MODE_OBS : (chk ? MODE - MODE_CHK : 0);
+    static constexpr bool eonly = obs && potsub == 3;  // MODE_OBS + 3: the energy sum alone (the rest came from a MODE_CHK sweep)
+    static constexpr int nred = eonly ? 1 : (obs ? 4 : (chk ? 3 : MODE));
+    static constexpr int nacc = nred > 0 ? nred : 1;
+};
+struct Extra {
+    const double* q[MAX_FUSED_LOWERS];  // stored states for the fused overlaps
+    const double* potsub_arr;           // pot_sub array in the slab layout (potential.rs:135-144), or NULL
+    double potsub;                      // pot_sub scalar (potential.rs:148-152)
+    int nb_total, bid_off;              // partial-sum row length / this launch's first column when several launches share a row
+};
+
+// cold path of the energy integrand: plain IEEE division (grid.rs:325-332)
+__device__ __noinline__ double energy_safe(double v, double w, double s, double den) {
+    return D_SUB(D_MUL(D_MUL(v, w), w), D_DIV(D_MUL(w, s), den));
+}
+
+template <int E, int MODE, int PHASE>
 __device__ __forceinline__ void iteration(Smem<E>& sm, double2 (&q)[2][Cfg<E>::N], int t, int T, const Lane1& ln,
                                           const Tile1& tl, int row_pitch, double*& orow, long long plane_elems, double dt,
-                                          const DivConst& dc, double& acc) {
+                                          const DivConst& dc, double (&acc)[Mode<MODE>::nacc], const Extra& ex,
+                                          const double* out_base, double xc0) {
     using C = Cfg<E>;
+    using M = Mode<MODE>;
     constexpr int BW = C::BW;
     const int s_new = t % C::NST;
     tb::mbar_wait(&sm.full[s_new], (t / C::NST) & 1);
@@ -84,6 +119,11 @@ __device__ __forceinline__ void iteration(Smem<E>& sm, double2 (&q)[2][Cfg<E>::N
         constexpr int IC = qslot<E>(PHASE, E);
         const bool nofast = !dc.fast;
         const double hdt = D_MUL(dt, 0.5);
+        double xx2 = 0.0;
+        if (M::obs || M::chk) {  // (global x of the output plane - centre)^2; the plane is xa - 2E + t
+            const double dx = D_ADD(xc0, (double)t);
+            xx2 = D_MUL(dx, dx);
+        }
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
             const double* row = psc + (s + E) * BW;
@@ -113,23 +153,64 @@ __device__ __forceinline__ void iteration(Smem<E>& sm, double2 (&q)[2][Cfg<E>::N
             const double s0 = Lap<E>::sum(xp0, xm0, yp0, ym0, zp0, zm0, w.x);
             const double s1 = Lap<E>::sum(xp1, xm1, yp1, ym1, zp1, zm1, w.y);
             const double2 vv = *reinterpret_cast<const double2*>(vs + s * BW);
-            unsigned b0 = 0u, b1 = 0u;
-            double a0, bd0, a1, bd1;
-            tb::ab_fast(vv.x, hdt, dt, a0, bd0, b0);
-            tb::ab_fast(vv.y, hdt, dt, a1, bd1, b1);
-            double2 r;
-            r.x = tb::update_fast(w.x, a0, bd0, s0, dc, b0);
-            r.y = tb::update_fast(w.y, a1, bd1, s1, dc, b1);
             const bool row_ok = tl.yin[s];
             const bool w0 = row_ok && ln.st0, w1 = row_ok && ln.st1;
-            if ((w0 && (b0 || nofast)) || (w1 && (b1 || nofast))) {  // cold: an operand left the fast-division window
-                r.x = tb::site_safe(w.x, vv.x, s0, dt, dc.den).u;
-                r.y = tb::site_safe(w.y, vv.y, s1, dt, dc.den).u;
-            }
-            if (w0) {
-                if (!w1) r.y = 0.0;  // odd nz: the pad column keeps its zero
-                *reinterpret_cast<double2*>(orow + s * row_pitch) = r;
-                if (NORM) acc = D_ADD(acc, D_ADD(D_MUL(r.x, r.x), D_MUL(r.y, r.y)));
+            unsigned b0 = 0u, b1 = 0u;
+            if (M::obs) {
+                // grid.rs:325-332: ((v w) w) - ((w S)/den); the pad column of an odd nz holds psi = 0 and adds exact zeros
+                double e0 = D_SUB(D_MUL(D_MUL(vv.x, w.x), w.x), tb::div_fast(D_MUL(w.x, s0), dc, b0));
+                double e1 = D_SUB(D_MUL(D_MUL(vv.y, w.y), w.y), tb::div_fast(D_MUL(w.y, s1), dc, b1));
+                if (w0) {
+                    if (b0 || b1 || nofast) {
+                        e0 = energy_safe(vv.x, w.x, s0, dc.den);
+                        e1 = energy_safe(vv.y, w.y, s1, dc.den);
+                    }
+                    acc[0] = D_ADD(acc[0], D_ADD(e0, e1));
+                }
+                if (w0 && !M::eonly) {
+                    const double ww0 = D_MUL(w.x, w.x), ww1 = D_MUL(w.y, w.y);
+                    acc[1] = D_ADD(acc[1], D_ADD(ww0, ww1));
+                    if (M::potsub == 1) acc[2] = D_ADD(acc[2], D_ADD(D_MUL(ww0, ex.potsub), D_MUL(ww1, ex.potsub)));
+                    if (M::potsub == 2) {
+                        const double2 ps = __ldg(reinterpret_cast<const double2*>(ex.potsub_arr + ((orow - out_base) + s * row_pitch)));
+                        acc[2] = D_ADD(acc[2], D_ADD(D_MUL(ww0, ps.x), D_MUL(ww1, ps.y)));
+                    }
+                    const double r20 = D_ADD(D_ADD(xx2, ln.yy2[s]), ln.zz2[0]), r21 = D_ADD(D_ADD(xx2, ln.yy2[s]), ln.zz2[1]);
+                    acc[3] = D_ADD(acc[3], D_ADD(D_MUL(ww0, r20), D_MUL(ww1, r21)));
+                }
+            } else {
+                double a0, bd0, a1, bd1;
+                tb::ab_fast(vv.x, hdt, dt, a0, bd0, b0);
+                tb::ab_fast(vv.y, hdt, dt, a1, bd1, b1);
+                double2 r;
+                r.x = tb::update_fast(w.x, a0, bd0, s0, dc, b0);
+                r.y = tb::update_fast(w.y, a1, bd1, s1, dc, b1);
+                if ((w0 && (b0 || nofast)) || (w1 && (b1 || nofast))) {  // cold: an operand left the fast-division window
+                    r.x = tb::site_safe(w.x, vv.x, s0, dt, dc.den).u;
+                    r.y = tb::site_safe(w.y, vv.y, s1, dt, dc.den).u;
+                }
+                if (w0) {
+                    if (!w1) r.y = 0.0;  // odd nz: the pad column keeps its zero
+                    *reinterpret_cast<double2*>(orow + s * row_pitch) = r;
+                    if (M::chk) {
+                        const double ww0 = D_MUL(r.x, r.x), ww1 = D_MUL(r.y, r.y);
+                        acc[0] = D_ADD(acc[0], D_ADD(ww0, ww1));
+                        if (M::potsub == 1) acc[1] = D_ADD(acc[1], D_ADD(D_MUL(ww0, ex.potsub), D_MUL(ww1, ex.potsub)));
+                        if (M::potsub == 2) {
+                            const double2 ps = __ldg(reinterpret_cast<const double2*>(ex.potsub_arr + ((orow - out_base) + s * row_pitch)));
+                            acc[1] = D_ADD(acc[1], D_ADD(D_MUL(ww0, ps.x), D_MUL(ww1, ps.y)));
+                        }
+                        const double r20 = D_ADD(D_ADD(xx2, ln.yy2[s]), ln.zz2[0]), r21 = D_ADD(D_ADD(xx2, ln.yy2[s]), ln.zz2[1]);
+                        acc[2] = D_ADD(acc[2], D_ADD(D_MUL(ww0, r20), D_MUL(ww1, r21)));
+                    } else {
+                        if (M::nred >= 1) acc[0] = D_ADD(acc[0], D_ADD(D_MUL(r.x, r.x), D_MUL(r.y, r.y)));
+#pragma unroll
+                        for (int i = 1; i < M::nred; ++i) {  // the stored states share psi's layout: same element offset
+                            const double2 ql = __ldg(reinterpret_cast<const double2*>(ex.q[i - 1] + ((orow - out_base) + s * row_pitch)));
+                            acc[i] = D_ADD(acc[i], D_ADD(D_MUL(ql.x, r.x), D_MUL(ql.y, r.y)));
+                        }
+                    }
+                }
             }
         }
     }
@@ -138,10 +219,11 @@ __device__ __forceinline__ void iteration(Smem<E>& sm, double2 (&q)[2][Cfg<E>::N
     (void)T;
 }
 
-template <int E, bool NORM, int... PH>
+template <int E, int MODE, int... PH>
 __device__ __forceinline__ void run_phases(std::integer_sequence<int, PH...>, Smem<E>& sm, double2 (&q)[2][Cfg<E>::N], int t0,
                                            int T, const Lane1& ln, const Tile1& tl, int row_pitch, double*& orow,
-                                           long long plane_elems, double dt, const DivConst& dc, double& acc,
+                                           long long plane_elems, double dt, const DivConst& dc,
+                                           double (&acc)[Mode<MODE>::nacc], const Extra& ex, const double* out_base, double xc0,
                                            const CUtensorMap* tm_psi, const CUtensorMap* tm_v, int z0, int y0, int gx) {
     using C = Cfg<E>;
     // after iteration t-1 has been finished by every thread, the stage of its centre plane is free: refill it
@@ -157,16 +239,18 @@ __device__ __forceinline__ void run_phases(std::integer_sequence<int, PH...>, Sm
             }
         }
     };
-    ((t0 + PH < T ? (iteration<E, NORM, PH>(sm, q, t0 + PH, T, ln, tl, row_pitch, orow, plane_elems, dt, dc, acc), refill(t0 + PH))
+    ((t0 + PH < T ? (iteration<E, MODE, PH>(sm, q, t0 + PH, T, ln, tl, row_pitch, orow, plane_elems, dt, dc, acc, ex, out_base, xc0), refill(t0 + PH))
                   : void()),
      ...);
 }
 
-template <int E, bool NORM>
+// `out`: the output field; in the observables modes the INPUT field itself (only its address arithmetic is used)
+template <int E, int MODE>
 __global__ void __launch_bounds__(Cfg<E>::THREADS, 1)
     sweep_tma1_kernel(const __grid_constant__ CUtensorMap tm_psi, const __grid_constant__ CUtensorMap tm_v,
                       double* __restrict__ out, Geom g, int xb, int xe, int xchunk, double dt, double den, int den_ok,
-                      double* __restrict__ partials) {
+                      double* __restrict__ partials, Extra ex) {
+    using M = Mode<MODE>;
     using C = Cfg<E>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     Smem<E>& sm = *reinterpret_cast<Smem<E>*>(smem_raw);
@@ -204,6 +288,17 @@ __global__ void __launch_bounds__(Cfg<E>::THREADS, 1)
     ln.st1 = col && (gz + 1) < g.nz;
 #pragma unroll
     for (int s = 0; s < 2; ++s) tl.yin[s] = (y0 + 2 * warp + s) < g.ny;
+    // potential.rs:366-371 on global WORK indices: d = idx - (N + 1)/2 per axis
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const double dy = D_SUB((double)(y0 + 2 * warp + s), D_DIV(D_ADD((double)g.gny, 1.), 2.));
+        const double dz = D_SUB((double)(gz + s), D_DIV(D_ADD((double)g.gnz, 1.), 2.));
+        ln.yy2[s] = D_MUL(dy, dy);
+        ln.zz2[s] = D_MUL(dz, dz);
+    }
+    // x offset of the output plane of iteration t from the centre: (x0 + xa - 2E + t) - (gnx + 1)/2 = xc0 + t, exact in
+    // f64 (integers and half-integers far below 2^52)
+    const double xc0 = D_SUB((double)(g.x0 + tl.xa - 2 * E), D_DIV(D_ADD((double)g.gnx, 1.), 2.));
     // running store pointer: the lane's pair in slot 0's row of the output plane of iteration t (= xa - 2E + t)
     double* orow = out + g.off(tl.xa - 2 * E, y0 + 2 * warp, 0) + gz;
 
@@ -212,18 +307,19 @@ __global__ void __launch_bounds__(Cfg<E>::THREADS, 1)
     for (int s = 0; s < 2; ++s)
 #pragma unroll
         for (int j = 0; j < C::N; ++j) q[s][j] = make_double2(0., 0.);
-    double acc = 0.0;
+    double acc[M::nacc];
+#pragma unroll
+    for (int i = 0; i < M::nacc; ++i) acc[i] = 0.0;
 
 #pragma unroll 1
     for (int t0 = 0; t0 < T; t0 += C::N)
-        run_phases<E, NORM>(std::make_integer_sequence<int, C::N>{}, sm, q, t0, T, ln, tl, g.zp, orow, g.plane, dt, dc, acc,
-                            &tm_psi, &tm_v, z0, y0, g.gx);
+        run_phases<E, MODE>(std::make_integer_sequence<int, C::N>{}, sm, q, t0, T, ln, tl, g.zp, orow, g.plane, dt, dc, acc,
+                            ex, out, xc0, &tm_psi, &tm_v, z0, y0, g.gx);
 
-    if (NORM) {
-        double a1[1] = {acc};
+    if (M::nred > 0) {
         const int nb = gridDim.x * gridDim.y * gridDim.z;
         const int bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
-        block_reduce_store<1>(a1, partials, nb, bid);
+        block_reduce_store<M::nacc>(acc, partials, ex.nb_total ? ex.nb_total : nb, ex.bid_off + bid);
     }
 }
 

@@ -26,7 +26,10 @@ namespace {
 std::string g_create_error;
 
 // scalar slots in ctx->scal (device doubles)
-enum { SL_OBS = 0, SL_NORM = 4, SL_TMP = 5, SL_DOT = 8, SL_COUNT = 8 + 256 };
+// SL_RAW: [0] = sum psi^2 of the last excited-state sweep, [1 + i] = raw overlap sum q_i psi; SL_COEF: Gram-Schmidt s_i
+// SL_CHK: [sum psi^2, sum psi^2 potsub, sum psi^2 r2] left by the last sweep of a ground-state evolve (MODE_CHK)
+enum { SL_OBS = 0, SL_NORM = 4, SL_TMP = 5, SL_CHK = 8, SL_RAW = 16, SL_COEF = 16 + 256, SL_COUNT = 16 + 512 };
+constexpr int GRAM_LD = 256;  // at most 255 stored states (wavenum is a u8)
 }  // namespace
 
 struct wafer_ctx {
@@ -48,6 +51,8 @@ struct wafer_ctx {
     int potsub_mode = 0;
     double potsub_scalar = 0.0;
     std::vector<double*> lowers;
+    bool chk_valid = false;    // scal[SL_CHK..] holds the point-wise check sums of the CURRENT psi (this rank's share)
+    double* gram = nullptr;    // G[i][j] = <q_i, q_j>, j < i, of the stored states (device, GRAM_LD x GRAM_LD)
     // host <-> device: two small bounce buffers in the host layout, filled / drained on s_copy while the
     // pack / unpack kernel of the other one runs on s_main (lazily allocated, never a field-sized buffer)
     double* stg[2] = {nullptr, nullptr};
@@ -168,14 +173,14 @@ int simple_blocks(const wafer_ctx* ctx, int xb, int xe) {
 }
 
 // forward declarations of the TMA one-step path (defined below, next to the tensor-map helpers)
-template <int E> int launch_sweep_t1(wafer_ctx* ctx, int src, int xb, int xe, bool norm, cudaStream_t st);
+template <int E> int launch_sweep_t1(wafer_ctx* ctx, int src, int xb, int xe, int mode, cudaStream_t st, int nb_total, int bid_off);
 template <int E> int t1_blocks(const wafer_ctx* ctx, int xb, int xe);
 
 // number of per-CTA partial sums the fused-norm sweep over [xb, xe) leaves in ctx->partials
 int sweep_blocks(const wafer_ctx* ctx, int xb, int xe);
 
-int launch_sweep(wafer_ctx* ctx, const double* cur, double* nxt, int xb, int xe, bool norm, long long part_off,
-                 cudaStream_t st);
+int launch_sweep(wafer_ctx* ctx, const double* cur, double* nxt, int xb, int xe, int nred, long long part_off,
+                 cudaStream_t st, int nb_total = 0, int bid_off = 0);
 
 int launch_sweep_plain(wafer_ctx* ctx, const double* cur, double* nxt, int xb, int xe, bool norm, long long part_off,
                        cudaStream_t st) {
@@ -274,22 +279,28 @@ int t1_chunks(const wafer_ctx* ctx, int planes) {
     return best_nc;
 }
 
+// every instantiated mode of the TMA one-step kernel (sweep_tma1.cuh): sweeps with 0..5 running sums, observables with
+// pot_sub none / scalar / array / energy only, sweeps that also leave the check's point-wise sums
+#define T1_MODES(X) X(0) X(1) X(2) X(3) X(4) X(5) X(8) X(9) X(10) X(11) X(16) X(17) X(18)
+
 template <int E>
 int init_t1_e(wafer_ctx* ctx) {
     TRY(make_tensor_map(ctx, &ctx->t1_psi[0], ctx->psi[0], t1::Cfg<E>::R0));
     TRY(make_tensor_map(ctx, &ctx->t1_psi[1], ctx->psi[1], t1::Cfg<E>::R0));
     TRY(make_tensor_map(ctx, &ctx->t1_v, ctx->v, t1::Cfg<E>::TY));
-    CK(cudaFuncSetAttribute(t1::sweep_tma1_kernel<E, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(t1::Smem<E>)));
-    CK(cudaFuncSetAttribute(t1::sweep_tma1_kernel<E, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(t1::Smem<E>)));
+    const int smem = (int)sizeof(t1::Smem<E>);
+#define T1_ATTR(M) CK(cudaFuncSetAttribute(t1::sweep_tma1_kernel<E, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    T1_MODES(T1_ATTR)
+#undef T1_ATTR
     return WAFER_OK;
 }
 
 int init_t1(wafer_ctx* ctx) {
     ctx->use_t1 = false;
-    // default on a single GPU (validated bit-for-bit there, 13-24 % faster for 5/7-point, profiles/r1_tma1_one_step.md);
-    // multi-rank contexts keep the register-queue kernel for their one-step passes unless the flag asks for it
+    // the default one-step kernel whenever V is kept on the fly (13-24 % faster than the register-queue kernel for
+    // 5/7-point, profiles/r1_tma1_one_step.md); boundary / interior sub-range launches of slab runs use it too
     const bool asked = (ctx->p.flags & WAFER_FLAG_TMA_ONE_STEP) != 0;
-    const bool by_default = ctx->world == 1 && !(ctx->p.flags & WAFER_FLAG_SIMPLE_SWEEP);
+    const bool by_default = !(ctx->p.flags & WAFER_FLAG_SIMPLE_SWEEP);
     if (!ctx->onfly || !(asked || by_default)) return WAFER_OK;
     if (ctx->p.ext == 1) TRY(init_t1_e<1>(ctx));
     else if (ctx->p.ext == 2) TRY(init_t1_e<2>(ctx));
@@ -300,19 +311,35 @@ int init_t1(wafer_ctx* ctx) {
     return WAFER_OK;
 }
 
+// mode (sweep_tma1.cuh): 0 plain sweep; 1 fused sum psi'^2; 1 + k: additionally the overlaps with stored states
+// 0..k-1 (k <= 4); MODE_OBS + p: observables of psi[src], nothing stored; MODE_CHK + p: sweep + the check's point-wise sums.
+// nb_total / bid_off: several launches (boundary + interior planes) share one row of per-CTA partial sums.
 template <int E>
-int launch_sweep_t1(wafer_ctx* ctx, int src, int xb, int xe, bool norm, cudaStream_t st) {
+int launch_sweep_t1(wafer_ctx* ctx, int src, int xb, int xe, int mode, cudaStream_t st, int nb_total, int bid_off) {
     if (xe <= xb) return WAFER_OK;
     const Geom& g = ctx->g;
     const int planes = xe - xb, chunk = ceil_div(planes, t1_chunks<E>(ctx, planes));
     dim3 grid(ceil_div(g.nz, t1::Cfg<E>::TZ), ceil_div(g.ny, t1::Cfg<E>::TY), ceil_div(planes, chunk));
     const size_t smem = sizeof(t1::Smem<E>);
-    if (norm)
-        t1::sweep_tma1_kernel<E, true><<<grid, t1::Cfg<E>::THREADS, smem, st>>>(ctx->t1_psi[src], ctx->t1_v, ctx->psi[src ^ 1], g, xb, xe,
-                                                                               chunk, ctx->p.dt, denominator(ctx), ctx->den_ok, ctx->partials);
-    else
-        t1::sweep_tma1_kernel<E, false><<<grid, t1::Cfg<E>::THREADS, smem, st>>>(ctx->t1_psi[src], ctx->t1_v, ctx->psi[src ^ 1], g, xb, xe,
-                                                                                chunk, ctx->p.dt, denominator(ctx), ctx->den_ok, ctx->partials);
+    t1::Extra ex{};
+    if (mode < t1::MODE_OBS)
+        for (int i = 0; i + 1 < mode; ++i) ex.q[i] = ctx->lowers[i];
+    ex.potsub_arr = ctx->potsub_arr;
+    ex.potsub = ctx->potsub_scalar;
+    ex.nb_total = nb_total;
+    ex.bid_off = bid_off;
+    // the observables modes read psi[src] and store nothing: `out` only anchors the element offsets
+    double* out = (mode >= t1::MODE_OBS && mode < t1::MODE_CHK) ? ctx->psi[src] : ctx->psi[src ^ 1];
+#define T1_CASE(M)                                                                                                              \
+    case M:                                                                                                                     \
+        t1::sweep_tma1_kernel<E, M><<<grid, t1::Cfg<E>::THREADS, smem, st>>>(ctx->t1_psi[src], ctx->t1_v, out, g, xb, xe, chunk,      \
+                                                                             ctx->p.dt, denominator(ctx), ctx->den_ok, ctx->partials, ex); \
+        break;
+    switch (mode) {
+        T1_MODES(T1_CASE)
+        default: ctx->err = "internal: unknown mode of the TMA one-step kernel"; return WAFER_ERR_INVALID;
+    }
+#undef T1_CASE
     return post_launch(ctx);
 }
 
@@ -327,16 +354,17 @@ int sweep_blocks(const wafer_ctx* ctx, int xb, int xe) {
     return ctx->p.ext == 1 ? t1_blocks<1>(ctx, xb, xe) : (ctx->p.ext == 2 ? t1_blocks<2>(ctx, xb, xe) : t1_blocks<3>(ctx, xb, xe));
 }
 
-// one lattice step cur -> nxt for planes [xb, xe): TMA-pipelined kernel when enabled, register-queue kernel otherwise
-int launch_sweep(wafer_ctx* ctx, const double* cur, double* nxt, int xb, int xe, bool norm, long long part_off,
-                 cudaStream_t st) {
-    if (!ctx->use_t1) return launch_sweep_plain(ctx, cur, nxt, xb, xe, norm, part_off, st);
+// one lattice step cur -> nxt for planes [xb, xe): TMA-pipelined kernel when enabled, register-queue kernel otherwise.
+// nred > 1 (fused overlaps) is only available in the TMA kernel: callers ask fused_lowers() first.
+int launch_sweep(wafer_ctx* ctx, const double* cur, double* nxt, int xb, int xe, int nred, long long part_off,
+                 cudaStream_t st, int nb_total, int bid_off) {
+    if (!ctx->use_t1) return launch_sweep_plain(ctx, cur, nxt, xb, xe, nred > 0, part_off, st);
     const int src = cur == ctx->psi[0] ? 0 : 1;
     if (nxt != ctx->psi[src ^ 1]) { ctx->err = "internal: sweep buffers are not the ping-pong pair"; return WAFER_ERR_INVALID; }
     switch (ctx->p.ext) {
-        case 1: return launch_sweep_t1<1>(ctx, src, xb, xe, norm, st);
-        case 2: return launch_sweep_t1<2>(ctx, src, xb, xe, norm, st);
-        default: return launch_sweep_t1<3>(ctx, src, xb, xe, norm, st);
+        case 1: return launch_sweep_t1<1>(ctx, src, xb, xe, nred, st, nb_total, bid_off);
+        case 2: return launch_sweep_t1<2>(ctx, src, xb, xe, nred, st, nb_total, bid_off);
+        default: return launch_sweep_t1<3>(ctx, src, xb, xe, nred, st, nb_total, bid_off);
     }
 }
 
@@ -386,40 +414,127 @@ int exchange(wafer_ctx* ctx, double* buf, cudaStream_t st) {
     return WAFER_OK;
 }
 
-// ---- Gram-Schmidt chain (grid.rs:477-492), optionally preceded by the normalise of grid.rs:465-468 -------
-// norm_slot < 0: no normalise.  Each pass fuses "psi -= q_{i-1} s_{i-1}" with the next overlap sum.
-template <bool N, bool A, bool D>
-int launch_gs(wafer_ctx* ctx, double* psi, int norm_slot, const double* qp, int sp_slot, const double* qn) {
+// ---- normalise + Gram-Schmidt (grid.rs:465-492) in two passes: see kernels.cuh (dots / coefficients / projection) ----
+LowerPtrs lower_group(const wafer_ctx* ctx, int first, int count) {
+    LowerPtrs lw{};
+    for (int i = 0; i < count; ++i) lw.q[i] = ctx->lowers[first + i];
+    return lw;
+}
+
+// raw overlaps of `psi` with stored states [first, first+count), count <= GS_GROUP -> scal[SL_RAW + 1 + first ...]
+int dots_group(wafer_ctx* ctx, const double* psi, int first, int count) {
     const Geom& g = ctx->g;
-    const long long n2 = g.total() / 2;
     const long long ob = (long long)g.gx * g.plane / 2, oe = (long long)(g.gx + g.L) * g.plane / 2;
-    const int grid = ew_grid(ctx, n2);
-    gs_pass_kernel<N, A, D><<<grid, EW_THREADS, 0, ctx->s_main>>>(
-        psi, n2, norm_slot >= 0 ? ctx->scal + norm_slot : nullptr, qp, sp_slot >= 0 ? ctx->scal + sp_slot : nullptr, qn,
-        ob, oe, ctx->partials);
+    const int grid = ew_grid(ctx, oe - ob);
+    const LowerPtrs lw = lower_group(ctx, first, count);
+    switch (count) {
+        case 1: dots_kernel<1><<<grid, EW_THREADS, 0, ctx->s_main>>>(psi, lw, ob, oe, ctx->partials); break;
+        case 2: dots_kernel<2><<<grid, EW_THREADS, 0, ctx->s_main>>>(psi, lw, ob, oe, ctx->partials); break;
+        case 3: dots_kernel<3><<<grid, EW_THREADS, 0, ctx->s_main>>>(psi, lw, ob, oe, ctx->partials); break;
+        default: dots_kernel<4><<<grid, EW_THREADS, 0, ctx->s_main>>>(psi, lw, ob, oe, ctx->partials); break;
+    }
+    TRY(post_launch(ctx));
+    gs_coeff_kernel<true, false><<<1, 1024, 0, ctx->s_main>>>(ctx->partials, grid, count, ctx->scal + SL_RAW + 1 + first, 0, nullptr,
+                                                                nullptr, nullptr, 0, nullptr);
     return post_launch(ctx);
 }
 
-int gs_chain(wafer_ctx* ctx, int norm_slot, int wnum) {
-    double* psi = ctx->psi[ctx->cur];
+int project(wafer_ctx* ctx, double* psi, const double* norm2_ptr, int wnum) {
     const long long n2 = ctx->g.total() / 2;
     const int grid = ew_grid(ctx, n2);
     if (wnum == 0) {
-        if (norm_slot >= 0) TRY((launch_gs<true, false, false>(ctx, psi, norm_slot, nullptr, -1, nullptr)));
+        if (norm2_ptr) {
+            project_kernel<0, true><<<grid, EW_THREADS, 0, ctx->s_main>>>(psi, n2, norm2_ptr, LowerPtrs{}, nullptr);
+            TRY(post_launch(ctx));
+        }
         return WAFER_OK;
     }
-    if (norm_slot >= 0) TRY((launch_gs<true, false, true>(ctx, psi, norm_slot, nullptr, -1, ctx->lowers[0])));
-    else TRY((launch_gs<false, false, true>(ctx, psi, -1, nullptr, -1, ctx->lowers[0])));
-    TRY(finalize(ctx, 1, grid, SL_DOT, ctx->s_main));
-    for (int i = 1; i < wnum; ++i) {
-        TRY((launch_gs<false, true, true>(ctx, psi, -1, ctx->lowers[i - 1], SL_DOT + i - 1, ctx->lowers[i])));
-        TRY(finalize(ctx, 1, grid, SL_DOT + i, ctx->s_main));
+    for (int first = 0; first < wnum; first += GS_GROUP) {
+        const int count = std::min(GS_GROUP, wnum - first);
+        const LowerPtrs lw = lower_group(ctx, first, count);
+        const double* coef = ctx->scal + SL_COEF + first;
+        const bool nrm = first == 0 && norm2_ptr;
+#define PROJ(K)                                                                                                  \
+    if (nrm) project_kernel<K, true><<<grid, EW_THREADS, 0, ctx->s_main>>>(psi, n2, norm2_ptr, lw, coef);        \
+    else project_kernel<K, false><<<grid, EW_THREADS, 0, ctx->s_main>>>(psi, n2, nullptr, lw, coef)
+        switch (count) {
+            case 1: PROJ(1); break;
+            case 2: PROJ(2); break;
+            case 3: PROJ(3); break;
+            default: PROJ(4); break;
+        }
+#undef PROJ
+        TRY(post_launch(ctx));
     }
-    return launch_gs<false, true, false>(ctx, psi, -1, ctx->lowers[wnum - 1], SL_DOT + wnum - 1, nullptr);
+    return WAFER_OK;
+}
+
+// psi <- normalise(psi, *norm2_ptr) (norm2_ptr == nullptr: skip) then orthogonalise against stored states [0, wnum).
+// have: the raw overlaps with the first `have` states (and, in raw[0], sum psi^2) already sit in ctx->partials as
+// rows 0..have of `sweep_nb` per-CTA partial sums, left there by the fused sweep.
+int gs_apply(wafer_ctx* ctx, double* psi, const double* norm2_ptr, int wnum, int have_rows = 0, int sweep_nb = 0) {
+    double* raw = ctx->scal + SL_RAW;
+    const bool one_launch = ctx->world == 1 && have_rows == wnum + 1;  // everything came out of the sweep: reduce + solve at once
+    if (one_launch) {
+        gs_coeff_kernel<true, true><<<1, 1024, 0, ctx->s_main>>>(ctx->partials, sweep_nb, have_rows, raw, wnum, raw + 1, norm2_ptr,
+                                                                   ctx->gram, GRAM_LD, ctx->scal + SL_COEF);
+        TRY(post_launch(ctx));
+        return project(ctx, psi, norm2_ptr, wnum);
+    }
+    if (have_rows > 0) {
+        gs_coeff_kernel<true, false><<<1, 1024, 0, ctx->s_main>>>(ctx->partials, sweep_nb, have_rows, raw, 0, nullptr, nullptr, nullptr,
+                                                                    0, nullptr);
+        TRY(post_launch(ctx));
+    }
+    for (int first = std::max(have_rows - 1, 0); first < wnum; first += GS_GROUP)
+        TRY(dots_group(ctx, psi, first, std::min(GS_GROUP, wnum - first)));
+    if (ctx->world > 1) {
+        // one all-reduce per step: [sum psi^2 (when the sweep produced it), overlaps 0..wnum)
+        const int off = have_rows > 0 ? 0 : 1, cnt = wnum + 1 - off;
+        if (cnt > 0) NK(nccl_api().AllReduce(raw + off, raw + off, cnt, kNcclFloat64, kNcclSum, ctx->comm, ctx->s_main));
+    }
+    if (wnum > 0) {
+        gs_coeff_kernel<false, true><<<1, 32, 0, ctx->s_main>>>(nullptr, 0, 0, raw, wnum, raw + 1, norm2_ptr, ctx->gram, GRAM_LD,
+                                                                  ctx->scal + SL_COEF);
+        TRY(post_launch(ctx));
+    }
+    return project(ctx, psi, norm2_ptr, wnum);
+}
+
+// a state joins the store: measure its overlaps with the states already there (row of the Gram matrix)
+int register_lower(wafer_ctx* ctx, double* q) {
+    if (!ctx->gram) CK(cudaMalloc(&ctx->gram, (size_t)GRAM_LD * GRAM_LD * sizeof(double)));
+    const int m = (int)ctx->lowers.size();
+    for (int first = 0; first < m; first += GS_GROUP) TRY(dots_group(ctx, q, first, std::min(GS_GROUP, m - first)));
+    if (m > 0) {
+        double* raw = ctx->scal + SL_RAW + 1;
+        if (ctx->world > 1) NK(nccl_api().AllReduce(raw, raw, m, kNcclFloat64, kNcclSum, ctx->comm, ctx->s_main));
+        CK(cudaMemcpyAsync(ctx->gram + (size_t)m * GRAM_LD, raw, m * sizeof(double), cudaMemcpyDeviceToDevice, ctx->s_main));
+    }
+    ctx->lowers.push_back(q);
+    return WAFER_OK;
 }
 
 int observables_device(wafer_ctx* ctx) {
     const Geom& g = ctx->g;
+    if (ctx->use_t1) {
+        // TMA-pipelined pass (sweep_tma1.cuh MODE_OBS): psi and V stream through the same shared-memory ring as the sweep
+        const int nb = sweep_blocks(ctx, 0, g.L);
+        if (ctx->chk_valid) {
+            // norm2, <pot_sub> and <r2> rode on the last sweep of evolve (grid.rs:405-437 are point-wise in psi): only the
+            // energy, which needs the neighbours of the final psi, is left
+            TRY(launch_sweep(ctx, ctx->psi[ctx->cur], ctx->psi[ctx->cur ^ 1], 0, g.L, t1::MODE_OBS + 3, 0, ctx->s_main));
+            gs_coeff_kernel<true, false><<<1, 1024, 0, ctx->s_main>>>(ctx->partials, nb, 1, ctx->scal + SL_OBS, 0, nullptr, nullptr,
+                                                                        nullptr, 0, nullptr);
+            TRY(post_launch(ctx));
+            CK(cudaMemcpyAsync(ctx->scal + SL_OBS + 1, ctx->scal + SL_CHK, 3 * sizeof(double), cudaMemcpyDeviceToDevice, ctx->s_main));
+            if (ctx->world > 1)
+                NK(nccl_api().AllReduce(ctx->scal + SL_OBS, ctx->scal + SL_OBS, 4, kNcclFloat64, kNcclSum, ctx->comm, ctx->s_main));
+            return WAFER_OK;
+        }
+        TRY(launch_sweep(ctx, ctx->psi[ctx->cur], ctx->psi[ctx->cur ^ 1], 0, g.L, t1::MODE_OBS + ctx->potsub_mode, 0, ctx->s_main));
+        return finalize(ctx, 4, nb, SL_OBS, ctx->s_main);
+    }
     dim3 grid(ceil_div(g.nz, SW_BX), ceil_div(g.ny, SW_BY), ceil_div(g.L, SW_XCH)), block(SW_BX, SW_BY);
     const int nb = grid.x * grid.y * grid.z;
     const double den = denominator(ctx);
@@ -651,7 +766,7 @@ int create_impl(const wafer_params* params, wafer_ctx* ctx) {
         {(long long)simple_blocks(ctx, 0, g.L) + 4 * simple_blocks(ctx, 0, g.e),
          (long long)ceil_div(g.nz, 56) * ceil_div(g.ny, 32) * std::min(g.L, 64),  // TMA one-step kernel: tiles x chunks
          (long long)ceil_div(g.nz, SW_BX) * ceil_div(g.ny, SW_BY) * ceil_div(g.L, SW_XCH), (long long)ctx->sm_count * 8});
-    ctx->partials_cap = nb * 4;
+    ctx->partials_cap = nb * 8;  // up to 1 + 4 fused running sums per CTA (sweep_tma1.cuh NRED), 4 for the observables
     CK(cudaMalloc(&ctx->partials, ctx->partials_cap * sizeof(double)));
     CK(cudaMalloc(&ctx->scal, SL_COUNT * sizeof(double)));
     CK(cudaMemsetAsync(ctx->scal, 0, SL_COUNT * sizeof(double), ctx->s_main));
@@ -711,7 +826,7 @@ int wafer_destroy(wafer_ctx* ctx) {
         if (ctx->ev_stg_full[b]) cudaEventDestroy(ctx->ev_stg_full[b]);
     }
     if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
-    cudaFree(ctx->d_cksum);
+    cudaFree(ctx->d_cksum); cudaFree(ctx->gram);
     cudaFree(ctx->potsub_arr); cudaFree(ctx->partials); cudaFree(ctx->scal); cudaFree(ctx->ring_flag);
     if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
     if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
@@ -754,6 +869,7 @@ int wafer_slab(const wafer_ctx* ctx, uint64_t* x0, uint64_t* x1) {
 // ---- state in / out ------------------------------------------------------------------------------------------
 int wafer_set_potential(wafer_ctx* ctx, const double* v_padded) {
     if (!ctx) return WAFER_ERR_INVALID;
+    ctx->chk_valid = false;  // psi (or what the check sums depend on) changes
     REQUIRE(v_padded, "v_padded is NULL");
     CK(cudaSetDevice(ctx->dev));
     TRY(upload_global(ctx, v_padded, ctx->v, false, false));
@@ -772,6 +888,7 @@ int wafer_get_potential(wafer_ctx* ctx, double* v_padded) {
 
 int wafer_set_pot_sub_scalar(wafer_ctx* ctx, double c) {
     if (!ctx) return WAFER_ERR_INVALID;
+    ctx->chk_valid = false;  // psi (or what the check sums depend on) changes
     // potential.rs:148-152: (None, Some(c)) only when c > 0, else (None, None)
     ctx->potsub_mode = c > 0.0 ? 1 : 0;
     ctx->potsub_scalar = c > 0.0 ? c : 0.0;
@@ -780,6 +897,7 @@ int wafer_set_pot_sub_scalar(wafer_ctx* ctx, double c) {
 
 int wafer_set_pot_sub_array(wafer_ctx* ctx, const double* work) {
     if (!ctx) return WAFER_ERR_INVALID;
+    ctx->chk_valid = false;  // psi (or what the check sums depend on) changes
     REQUIRE(work, "pot_sub array is NULL");
     CK(cudaSetDevice(ctx->dev));
     if (!ctx->potsub_arr) TRY(alloc_field(ctx, &ctx->potsub_arr));
@@ -790,6 +908,7 @@ int wafer_set_pot_sub_array(wafer_ctx* ctx, const double* work) {
 
 int wafer_set_phi(wafer_ctx* ctx, const double* phi_padded) {
     if (!ctx) return WAFER_ERR_INVALID;
+    ctx->chk_valid = false;  // psi (or what the check sums depend on) changes
     REQUIRE(phi_padded, "phi_padded is NULL");
     CK(cudaSetDevice(ctx->dev));
     const int rc = upload_global(ctx, phi_padded, ctx->psi[ctx->cur], false, true);
@@ -817,6 +936,7 @@ int wafer_slab_planes(const wafer_ctx* ctx, int32_t which, uint64_t* p0, uint64_
 
 int wafer_set_phi_slab(wafer_ctx* ctx, const double* chunk) {
     if (!ctx) return WAFER_ERR_INVALID;
+    ctx->chk_valid = false;  // psi (or what the check sums depend on) changes
     REQUIRE(chunk, "chunk is NULL");
     CK(cudaSetDevice(ctx->dev));
     long long hp0, hp1;
@@ -828,6 +948,7 @@ int wafer_set_phi_slab(wafer_ctx* ctx, const double* chunk) {
 
 int wafer_set_phi_owned(wafer_ctx* ctx, const double* chunk) {
     if (!ctx) return WAFER_ERR_INVALID;
+    ctx->chk_valid = false;  // psi (or what the check sums depend on) changes
     REQUIRE(chunk, "chunk is NULL");
     CK(cudaSetDevice(ctx->dev));
     long long hp0, hp1;
@@ -855,10 +976,10 @@ int wafer_push_lower(wafer_ctx* ctx, const double* q_padded) {
     CK(cudaSetDevice(ctx->dev));
     double* q = nullptr;
     TRY(alloc_field(ctx, &q));
-    const int rc = upload_global(ctx, q_padded, q, false, true);
-    if (rc != WAFER_OK) { cudaFree(q); return rc; }
-    ctx->lowers.push_back(q);
-    return WAFER_OK;
+    int rc = upload_global(ctx, q_padded, q, false, true);
+    if (rc == WAFER_OK) rc = register_lower(ctx, q);
+    if (rc != WAFER_OK) cudaFree(q);
+    return rc;
 }
 
 int wafer_push_lower_from_phi(wafer_ctx* ctx) {
@@ -869,8 +990,9 @@ int wafer_push_lower_from_phi(wafer_ctx* ctx) {
     double* q = nullptr;
     CK(cudaMalloc(&q, ctx->bytes()));
     CK(cudaMemcpyAsync(q, ctx->psi[ctx->cur], ctx->bytes(), cudaMemcpyDeviceToDevice, ctx->s_main));
-    ctx->lowers.push_back(q);
-    return WAFER_OK;
+    const int rc = register_lower(ctx, q);
+    if (rc != WAFER_OK) cudaFree(q);
+    return rc;
 }
 
 int wafer_get_lower(wafer_ctx* ctx, uint32_t idx, double* q_padded) {
@@ -882,6 +1004,7 @@ int wafer_get_lower(wafer_ctx* ctx, uint32_t idx, double* q_padded) {
 
 int wafer_phi_from_lower(wafer_ctx* ctx, uint32_t idx) {
     if (!ctx) return WAFER_ERR_INVALID;
+    ctx->chk_valid = false;  // psi (or what the check sums depend on) changes
     REQUIRE(idx < ctx->lowers.size(), "no such lower state");
     CK(cudaSetDevice(ctx->dev));
     CK(cudaMemcpyAsync(ctx->psi[ctx->cur], ctx->lowers[idx], ctx->bytes(), cudaMemcpyDeviceToDevice, ctx->s_main));
@@ -891,6 +1014,7 @@ int wafer_phi_from_lower(wafer_ctx* ctx, uint32_t idx) {
 
 int wafer_phi_seed_from_lower(wafer_ctx* ctx, uint32_t idx) {
     if (!ctx) return WAFER_ERR_INVALID;
+    ctx->chk_valid = false;  // psi (or what the check sums depend on) changes
     REQUIRE(idx < ctx->lowers.size(), "no such lower state");
     CK(cudaSetDevice(ctx->dev));
     const long long rows = (long long)(ctx->g.L + 2 * ctx->g.gx) * ctx->g.ny;
@@ -914,6 +1038,7 @@ uint32_t wafer_num_lowers(const wafer_ctx* ctx) { return ctx ? (uint32_t)ctx->lo
 
 int wafer_generate_potential(wafer_ctx* ctx, int32_t kind, double sig) {
     if (!ctx) return WAFER_ERR_INVALID;
+    ctx->chk_valid = false;  // psi (or what the check sums depend on) changes
     CK(cudaSetDevice(ctx->dev));
     GenParams gp = make_gen_params(ctx->p.dn, ctx->p.mass, sig);
     REQUIRE(potential_kind_supported(kind), "PotentialNotAvailable: no formula for this potential kind (potential.rs:315-317)");
@@ -927,6 +1052,7 @@ int wafer_generate_potential(wafer_ctx* ctx, int32_t kind, double sig) {
 
 int wafer_generate_initial_condition(wafer_ctx* ctx, int32_t kind) {
     if (!ctx) return WAFER_ERR_INVALID;
+    ctx->chk_valid = false;  // psi (or what the check sums depend on) changes
     REQUIRE(kind >= 2 && kind <= 4, "only Coulomb (2), Constant (3) and Boolean (4) can be generated on the device");
     CK(cudaSetDevice(ctx->dev));
     GenParams gp = make_gen_params(ctx->p.dn, ctx->p.mass, 0.0);
@@ -972,21 +1098,23 @@ int wafer_norm2(wafer_ctx* ctx, double* out) {
 
 int wafer_normalise(wafer_ctx* ctx, double norm2) {
     if (!ctx) return WAFER_ERR_INVALID;
+    ctx->chk_valid = false;  // psi (or what the check sums depend on) changes
     TRY(ready(ctx, false));
     CK(cudaSetDevice(ctx->dev));
     set_scalar_kernel<<<1, 1, 0, ctx->s_main>>>(ctx->scal + SL_TMP, norm2);
     TRY(post_launch(ctx));
-    return gs_chain(ctx, SL_TMP, 0);
+    return gs_apply(ctx, ctx->psi[ctx->cur], ctx->scal + SL_TMP, 0);
 }
 
 int wafer_orthogonalise(wafer_ctx* ctx, uint8_t wnum) {
     if (!ctx) return WAFER_ERR_INVALID;
+    ctx->chk_valid = false;  // psi (or what the check sums depend on) changes
     TRY(ready(ctx, false));
     // grid.rs:478: w_store.iter().take(wnum) — silently clamps to the stored count
     const int n = std::min<int>(wnum, (int)ctx->lowers.size());
     if (n == 0) return WAFER_OK;
     CK(cudaSetDevice(ctx->dev));
-    return gs_chain(ctx, -1, n);
+    return gs_apply(ctx, ctx->psi[ctx->cur], nullptr, n);
 }
 
 int wafer_evolve(wafer_ctx* ctx, uint8_t wnum_in, uint64_t steps) {
@@ -1005,12 +1133,20 @@ int wafer_evolve(wafer_ctx* ctx, uint8_t wnum_in, uint64_t steps) {
     }
     const uint64_t total = steps == 0 ? 1 : steps;  // grid.rs:562-686 is a do-while: steps == 0 still sweeps once
     const bool fused = overlap && ctx->p2p;  // halo stores fused into the boundary kernels (peer memory), no NCCL
+    // North-star "block reductions fused into the final sweep before each check": the LAST step of a ground-state evolve
+    // runs as a one-step sweep that also accumulates sum psi^2, sum psi^2 pot_sub and sum psi^2 r2 of its output; the
+    // check that follows then only needs the energy pass.  Worth one non-time-tiled pass only on long calls.
+    const bool fuse_chk = ctx->use_t1 && !excited && total >= 64 && !(ctx->p.flags & WAFER_FLAG_NO_FUSED_CHECK);
+    ctx->chk_valid = false;
+    int chk_nb = 0;
     const int has_lo = ctx->rank > 0, has_hi = ctx->rank < ctx->world - 1;
     uint64_t done = 0;
     while (done < total) {
         // ground state: two steps per HBM pass with the time-tiled TMA kernel whenever two steps remain;
         // excited states need a global norm / Gram-Schmidt after EVERY step (grid.rs:674-681): one step per pass
-        const bool two = ctx->use_tb && !excited && total - done >= 2;
+        const bool last = total - done == 1;
+        const bool two = ctx->use_tb && !excited && total - done >= 2 && !(fuse_chk && total - done == 2);
+        const int chk_mode = (fuse_chk && last) ? t1::MODE_CHK + ctx->potsub_mode : 0;
         const int b = g.gx;  // boundary planes = ghost depth the neighbours keep (2 for ThreePoint, else ext)
         const int src = ctx->cur;
         const double* cur = ctx->psi[src];
@@ -1036,8 +1172,11 @@ int wafer_evolve(wafer_ctx* ctx, uint8_t wnum_in, uint64_t steps) {
                 TRY(launch_sweep_tb2(ctx, src, 0, b, ctx->s_halo, plo, ctx->peer_L[0]));
                 TRY(launch_sweep_tb2(ctx, src, g.L - b, g.L, ctx->s_halo, phi_, -(long long)g.L));
             } else {
-                TRY(launch_sweep(ctx, cur, nxt, 0, b, false, 0, ctx->s_halo));
-                TRY(launch_sweep(ctx, cur, nxt, g.L - b, g.L, false, 0, ctx->s_halo));
+                // (final step with fused check sums: the three launches share one row of per-CTA partial sums)
+                const int nb_lo = sweep_blocks(ctx, 0, b), nb_hi = sweep_blocks(ctx, g.L - b, g.L);
+                chk_nb = chk_mode ? nb_lo + nb_hi + sweep_blocks(ctx, b, g.L - b) : 0;
+                TRY(launch_sweep(ctx, cur, nxt, 0, b, chk_mode, 0, ctx->s_halo, chk_nb, 0));
+                TRY(launch_sweep(ctx, cur, nxt, g.L - b, g.L, chk_mode, 0, ctx->s_halo, chk_nb, nb_lo));
                 if (fused) {  // rare odd tail step: plain peer copies of the boundary planes
                     const size_t bytes = (size_t)b * g.plane * sizeof(double);
                     if (plo) CK(cudaMemcpyAsync(plo + g.off(ctx->peer_L[0], -g.e, 0), nxt + g.off(0, -g.e, 0), bytes, cudaMemcpyDeviceToDevice, ctx->s_halo));
@@ -1053,18 +1192,20 @@ int wafer_evolve(wafer_ctx* ctx, uint8_t wnum_in, uint64_t steps) {
             }
             CK(cudaEventRecord(ctx->ev_halo, ctx->s_halo));
             if (two) TRY(launch_sweep_tb2(ctx, src, b, g.L - b, ctx->s_main));
-            else TRY(launch_sweep(ctx, cur, nxt, b, g.L - b, false, 0, ctx->s_main));
+            else TRY(launch_sweep(ctx, cur, nxt, b, g.L - b, chk_mode, 0, ctx->s_main, chk_nb, chk_nb - sweep_blocks(ctx, b, g.L - b)));
             CK(cudaEventRecord(ctx->ev_main, ctx->s_main));
         } else {
+            // excited states: sum psi'^2 and (TMA kernel) the overlaps with up to four stored states ride on the sweep
+            const int nred = !excited ? chk_mode : (ctx->use_t1 ? 1 + std::min(wnum, t1::MAX_FUSED_LOWERS) : 1);
+            if (chk_mode) chk_nb = sweep_blocks(ctx, 0, g.L);
             if (two) TRY(launch_sweep_tb2(ctx, src, 0, g.L, ctx->s_main));
-            else TRY(launch_sweep(ctx, cur, nxt, 0, g.L, excited, 0, ctx->s_main));
+            else TRY(launch_sweep(ctx, cur, nxt, 0, g.L, nred, 0, ctx->s_main));
             TRY(exchange(ctx, nxt, ctx->s_main));
+            ctx->cur ^= 1;
+            // grid.rs:674-681: norm2 -> normalise -> orthogonalise, every step
+            if (excited) TRY(gs_apply(ctx, nxt, ctx->scal + SL_RAW, wnum, nred, sweep_blocks(ctx, 0, g.L)));
         }
-        ctx->cur ^= 1;
-        if (excited) {
-            TRY(finalize(ctx, 1, sweep_blocks(ctx, 0, g.L), SL_NORM, ctx->s_main));
-            TRY(gs_chain(ctx, SL_NORM, wnum));
-        }
+        if (overlap) ctx->cur ^= 1;
         done += two ? 2 : 1;
     }
     if (overlap) {
@@ -1080,6 +1221,12 @@ int wafer_evolve(wafer_ctx* ctx, uint8_t wnum_in, uint64_t steps) {
         }
         CK(cudaStreamWaitEvent(ctx->s_main, ctx->ev_halo, 0));
     }
+    if (fuse_chk && chk_nb > 0) {
+        gs_coeff_kernel<true, false><<<1, 1024, 0, ctx->s_main>>>(ctx->partials, chk_nb, 3, ctx->scal + SL_CHK, 0, nullptr, nullptr,
+                                                                    nullptr, 0, nullptr);
+        TRY(post_launch(ctx));
+        ctx->chk_valid = true;
+    }
     return WAFER_OK;
 }
 
@@ -1090,7 +1237,8 @@ int wafer_check(wafer_ctx* ctx, uint8_t wnum_in, wafer_observables* out) {
     CK(cudaSetDevice(ctx->dev));
     const int wnum = std::min<int>(wnum_in, (int)ctx->lowers.size());
     TRY(observables_device(ctx));                // grid.rs:127
-    TRY(gs_chain(ctx, SL_OBS + 1, wnum));        // grid.rs:130 normalise(norm2) then 133-135 orthogonalise
+    TRY(gs_apply(ctx, ctx->psi[ctx->cur], ctx->scal + SL_OBS + 1, wnum));  // grid.rs:130 normalise(norm2), 133-135 orthogonalise
+    ctx->chk_valid = false;
     double s[4];
     TRY(read_scalars(ctx, SL_OBS, 4, s));
     out->energy = s[0]; out->norm2 = s[1]; out->v_infinity = s[2]; out->r2 = s[3];
