@@ -11,7 +11,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "generators.cuh"
@@ -32,6 +34,12 @@ enum { SL_OBS = 0, SL_NORM = 4, SL_TMP = 5, SL_CHK = 8, SL_RAW = 16, SL_COEF = 1
 constexpr int GRAM_LD = 256;  // at most 255 stored states (wavenum is a u8)
 }  // namespace
 
+struct Tb2Sched {  // work lists of the persistent time-tiled sweep for one plane range (device arrays, sweep_tb.cuh Sched)
+    tb::Segment *bulk = nullptr, *segs = nullptr;
+    int *first = nullptr, *counters = nullptr;
+    int ncta = 0, nbulk = 0;
+};
+
 struct wafer_ctx {
     wafer_params p{};
     Geom g{};
@@ -41,6 +49,7 @@ struct wafer_ctx {
     bool use_tb = false;            // time-tiled TMA sweep available (ThreePoint, V on the fly)
     CUtensorMap tm_psi[2], tm_v;    // TMA descriptors of the interior of psi[0], psi[1], v
     int den_ok = 0;
+    std::map<std::pair<int, int>, Tb2Sched> tb2_sched;  // keyed by the plane range [xb, xe)
     bool use_t1 = false;            // TMA-pipelined one-step sweep (WAFER_FLAG_TMA_ONE_STEP)
     CUtensorMap t1_psi[2], t1_v;
     cudaStream_t s_main = nullptr, s_halo = nullptr;
@@ -233,32 +242,145 @@ int init_tb(wafer_ctx* ctx) {
     return WAFER_OK;
 }
 
+// ---- work distribution of the time-tiled sweep (persistent grid; see sweep_tb.cuh Sched) ---------------------------
+// Every segment pays 4 plane-iterations of pipeline fill; CTAs that share a tile edge re-read each other's halo cells,
+// from L2 only if they pass the same planes at about the same time; and the SMs should finish together.
+//   * x is cut into chunks of at most 512 planes; per chunk, whole tile columns in tile order form the BULK list that the
+//     CTAs drain through an atomic counter (in-order dispatch keeps neighbouring tiles close in time);
+//   * of the last chunk, the ntiles % G columns that would leave most SMs idle in a last partial wave are cut along x
+//     into G equal shares (even lengths, no stubs shorter than 6 planes): the static TAIL of each CTA.
+// 512^3 on 148 SMs: one round of 148 columns + 14 columns cut 148 ways = 516 + ~53 plane-iterations per SM, against
+// 10 waves x 60 for round 1's uniform grid of 162 tiles x 9 chunks.  Measured (gpurun_out/r2f..r2j,
+// profiles/r2_tb2_variants.md): statically assigned rounds +4.8 % at 512^3 and +6 % on a 128-plane slab but -6 % at
+// 1024^3, where CTAs drift apart from round to round and the halo re-reads miss L2 (+17 % DRAM reads, ncu r2g); a fully
+// contiguous static split ("contig") -13 %.  WAFER_TB_SCHED=dynamic|rounds|legacy|contig selects the policy for A/B runs.
+int tb2_schedule(wafer_ctx* ctx, int xb, int xe, const Tb2Sched** out) {
+    auto it = ctx->tb2_sched.find({xb, xe});
+    if (it != ctx->tb2_sched.end()) { *out = &it->second; return WAFER_OK; }
+    const Geom& g = ctx->g;
+    const int ntz = ceil_div(g.nz, tb::TZ), nty = ceil_div(g.ny, tb::TY), ntiles = ntz * nty, P = xe - xb;
+    const int slots = ctx->sm_count * tb::CTAS_PER_SM;
+    std::vector<tb::Segment> bulk;
+    std::vector<std::vector<tb::Segment>> per;
+    auto seg = [&](int tile, int a, int b) { return tb::Segment{(tile / ntz) * tb::TY, (tile % ntz) * tb::TZ, a, b}; };
+    static const std::string mode = getenv("WAFER_TB_SCHED") ? getenv("WAFER_TB_SCHED") : "dynamic";
+    static const int MAXSEG = getenv("WAFER_TB_MAXSEG") ? std::max(8, atoi(getenv("WAFER_TB_MAXSEG"))) : 512;
+    const int MINSEG = 6;
+    int G = (int)std::max<long long>(1, std::min<long long>(slots, ((long long)ntiles * P + 7) / 8));
+    // shares of `cols` tile columns starting at tile `t0`, planes [ca, cz), cut into G equal runs -> per[k]
+    auto cut_static = [&](int t0, int cols, int ca, int cz) {
+        const int Pc = cz - ca;
+        const long long Ur = (long long)cols * Pc;
+        auto snap = [&](long long u) {
+            const long long p = u % Pc;
+            if (p == 0) return u;
+            if (p < MINSEG) return u - p;
+            if (Pc - p < MINSEG) return u + (Pc - p);
+            return u - (p & 1);
+        };
+        for (int k = 0; k < G && Ur > 0; ++k) {
+            long long u = snap(k * Ur / G);
+            const long long ue = k + 1 == G ? Ur : snap((k + 1) * Ur / G);
+            while (u < ue) {
+                const int p0 = (int)(u % Pc), len = (int)std::min<long long>(Pc - p0, ue - u);
+                per[k].push_back(seg(t0 + (int)(u / Pc), ca + p0, ca + p0 + len));
+                u += len;
+            }
+        }
+    };
+    if (mode == "legacy") {
+        // round 1's grid: tiles x chunks CTAs, one segment each, dispatched in order (here through the counter)
+        int best_nc = 1;
+        double best_cost = 1e300;
+        for (int nc = 1; nc <= std::min(P, 64); ++nc) {
+            const double cost = (double)ceil_div((long long)ntiles * nc, slots) * ((double)ceil_div(P, nc) + 3.0);
+            if (cost < best_cost * 0.999) { best_cost = cost; best_nc = nc; }
+        }
+        const int chunk = ceil_div(P, best_nc);
+        for (int c = 0; c * chunk < P; ++c)
+            for (int t = 0; t < ntiles; ++t) bulk.push_back(seg(t, xb + c * chunk, std::min(xe, xb + (c + 1) * chunk)));
+        G = (int)std::min<size_t>(slots, bulk.size());
+        per.resize(G);
+    } else if (mode == "contig") {
+        per.resize(G);
+        cut_static(0, ntiles, xb, xe);
+    } else {
+        per.resize(G);
+        // number of x chunks: at least P / MAXSEG; a few more if that leaves a smaller statically cut tail.  The tail runs
+        // out of lock step (its halo re-reads miss L2), which the estimate charges with an empirical factor of 1.6.
+        int nchunk = ceil_div(P, MAXSEG);
+        if (mode == "dynamic" && ntiles >= G) {
+            double best = 1e300;
+            for (int nc = ceil_div(P, MAXSEG); nc <= ceil_div(P, MAXSEG) + 6 && nc * 32 <= P; ++nc) {
+                const int ch = (ceil_div(P, nc) + 1) & ~1;
+                const long long items = (long long)nc * ntiles, rest = items % G;
+                const double cost = (double)(items / G) * (ch + 4) + (rest ? ((double)rest * ch / G + 4) * 1.6 : 0.0);
+                if (cost < best * 0.999) { best = cost; nchunk = nc; }
+            }
+        }
+        const int chunk = (ceil_div(P, nchunk) + 1) & ~1;
+        const int R = ntiles / G;
+        for (int c = 0; c * chunk < P; ++c) {
+            const int ca = xb + c * chunk, cz = std::min(xe, ca + chunk);
+            if (mode == "rounds") {  // static assignment of whole columns, round by round
+                for (int r = 0; r < R; ++r)
+                    for (int k = 0; k < G; ++k) per[k].push_back(seg(r * G + k, ca, cz));
+                cut_static(R * G, ntiles - R * G, ca, cz);
+            } else {                 // "dynamic": in-order dispatch of whole columns, chunk after chunk
+                for (int t = 0; t < ntiles; ++t) bulk.push_back(seg(t, ca, cz));
+            }
+        }
+        if (mode != "rounds") {
+            // the bulk must come out even — a multiple of G columns — or the CTAs that drew one column more finish a whole
+            // column late: the last bulk.size() % G columns (all in the last chunk) are cut into G equal static shares
+            const int rest = std::min((int)(bulk.size() % G), ntiles);  // (never reaches back into an earlier chunk)
+            if (rest > 0) {
+                const tb::Segment f = bulk[bulk.size() - rest];
+                const int t0 = (f.y0 / tb::TY) * ntz + f.z0 / tb::TZ;
+                bulk.resize(bulk.size() - rest);
+                cut_static(t0, rest, f.xa, f.xz);
+            }
+        }
+    }
+    std::vector<tb::Segment> flat;
+    std::vector<int> first{0};
+    for (const auto& v : per) {
+        flat.insert(flat.end(), v.begin(), v.end());
+        first.push_back((int)flat.size());
+    }
+    Tb2Sched sc;
+    sc.ncta = G;
+    sc.nbulk = (int)bulk.size();
+    CK(cudaMalloc(&sc.bulk, std::max<size_t>(bulk.size(), 1) * sizeof(tb::Segment)));
+    CK(cudaMalloc(&sc.segs, std::max<size_t>(flat.size(), 1) * sizeof(tb::Segment)));
+    CK(cudaMalloc(&sc.first, first.size() * sizeof(int)));
+    CK(cudaMalloc(&sc.counters, 2 * sizeof(int)));
+    CK(cudaMemsetAsync(sc.counters, 0, 2 * sizeof(int), ctx->s_main));
+    if (!bulk.empty()) CK(cudaMemcpyAsync(sc.bulk, bulk.data(), bulk.size() * sizeof(tb::Segment), cudaMemcpyHostToDevice, ctx->s_main));
+    if (!flat.empty()) CK(cudaMemcpyAsync(sc.segs, flat.data(), flat.size() * sizeof(tb::Segment), cudaMemcpyHostToDevice, ctx->s_main));
+    CK(cudaMemcpyAsync(sc.first, first.data(), first.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->s_main));
+    CK(cudaStreamSynchronize(ctx->s_main));  // the host vectors die here; any stream may launch with the schedule afterwards
+    *out = &(ctx->tb2_sched[{xb, xe}] = sc);
+    return WAFER_OK;
+}
+
 // two lattice steps: psi[src] -> psi[src^1] for planes [xb, xe); peer != nullptr: also store every output at the
 // same (plane + peer_plane_shift, row, column) of the neighbour's buffer `peer`
 int launch_sweep_tb2(wafer_ctx* ctx, int src, int xb, int xe, cudaStream_t st, double* peer = nullptr,
                      long long peer_plane_shift = 0) {
     if (xe <= xb) return WAFER_OK;
     const Geom& g = ctx->g;
-    // x chunking: every chunk pays ~3 plane-iterations of pipeline fill, and CTAs run in waves of one per SM.
-    // Pick the chunk count that minimises  waves(tiles * nc) * (planes / nc + fill).
-    const long long tiles = (long long)ceil_div(g.nz, tb::TZ) * ceil_div(g.ny, tb::TY);
-    const int planes = xe - xb, slots = ctx->sm_count * tb::CTAS_PER_SM;
-    int best_nc = 1;
-    double best_cost = 1e300;
-    for (int nc = 1; nc <= std::min(planes, 64); ++nc) {
-        const double cost = (double)ceil_div(tiles * nc, slots) * ((double)ceil_div(planes, nc) + 3.0);
-        if (cost < best_cost * 0.999) { best_cost = cost; best_nc = nc; }
-    }
-    const int chunk = ceil_div(planes, best_nc);
-    dim3 grid(ceil_div(g.nz, tb::TZ), ceil_div(g.ny, tb::TY), ceil_div(planes, chunk));
+    const Tb2Sched* sc = nullptr;
+    TRY(tb2_schedule(ctx, xb, xe, &sc));
     double* out = ctx->psi[src ^ 1];
+    const tb::Sched ks{sc->bulk, sc->nbulk, sc->segs, sc->first, sc->counters};
     if (peer) {
         const long long delta = (peer - out) + peer_plane_shift * g.plane;  // element distance local site -> peer site
-        tb::sweep_tb2_kernel<true><<<grid, tb::THREADS, tb::SMEM_BYTES, st>>>(ctx->tm_psi[src], ctx->tm_v, out, delta, g, xb, xe, chunk,
-                                                                              ctx->p.dt, denominator(ctx), ctx->den_ok);
+        tb::sweep_tb2_kernel<true><<<sc->ncta, tb::THREADS, tb::SMEM_BYTES, st>>>(ctx->tm_psi[src], ctx->tm_v, out, delta, g, ks,
+                                                                                  ctx->p.dt, denominator(ctx), ctx->den_ok);
     } else {
-        tb::sweep_tb2_kernel<false><<<grid, tb::THREADS, tb::SMEM_BYTES, st>>>(ctx->tm_psi[src], ctx->tm_v, out, 0, g, xb, xe, chunk,
-                                                                               ctx->p.dt, denominator(ctx), ctx->den_ok);
+        tb::sweep_tb2_kernel<false><<<sc->ncta, tb::THREADS, tb::SMEM_BYTES, st>>>(ctx->tm_psi[src], ctx->tm_v, out, 0, g, ks,
+                                                                                   ctx->p.dt, denominator(ctx), ctx->den_ok);
     }
     return post_launch(ctx);
 }
@@ -827,6 +949,9 @@ int wafer_destroy(wafer_ctx* ctx) {
     }
     if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
     cudaFree(ctx->d_cksum); cudaFree(ctx->gram);
+    for (auto& kv : ctx->tb2_sched) {
+        cudaFree(kv.second.bulk); cudaFree(kv.second.segs); cudaFree(kv.second.first); cudaFree(kv.second.counters);
+    }
     cudaFree(ctx->potsub_arr); cudaFree(ctx->partials); cudaFree(ctx->scal); cudaFree(ctx->ring_flag);
     if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
     if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
