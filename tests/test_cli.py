@@ -56,6 +56,11 @@ def test_config_checks_follow_the_reference(binary, tmp_path):
     assert c["max_steps"] == 5000 and c["output"]["snap_update"] == 2000
     r = _check(binary, base.replace("central_difference: ThreePoint", "central_difference: SevenPoint"), tmp_path)
     assert json.loads(r.stdout)["ext"] == 3
+    # refused when the configuration is read, not hours later when a converged state is about to be saved
+    r = _check(binary, base.replace("file_type: Json", "file_type: Yaml"), tmp_path)
+    assert r.returncode == 1 and "not supported by this build" in r.stderr
+    r = _check(binary, base.replace("# snap_update: 10000", "snap_update: 0"), tmp_path)
+    assert r.returncode == 1 and "snap_update must be positive" in r.stderr
 
 
 @pytest.mark.skipif(os.path.exists("/dev/nvidiactl"), reason="a GPU is present")

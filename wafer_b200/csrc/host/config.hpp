@@ -172,7 +172,12 @@ inline Config load_config(std::istream& in) {
     c.wavemax = (unsigned)wm;
     c.screen_update = to_u64(need("output.screen_update"), "output.screen_update");
     if (auto s = opt("output.snap_update")) c.snap_update = to_u64(*s, "output.snap_update");
+    // the reference computes step % snap_update (grid.rs:137): 0 would be a division by zero there too — refuse it up front
+    if (c.snap_update && *c.snap_update == 0) throw ConfigError("output.snap_update must be positive when given");
     c.file_type = enum_index(filetype_names(), need("output.file_type"), "output.file_type");
+    // Yaml / Ron array files are valid in the reference but not written by this front end: say so before any GPU work,
+    // not when a converged wavefunction is about to be saved
+    if (c.file_type > 2) throw ConfigError("output.file_type " + filetype_names()[c.file_type] + " is not supported by this build (use Messagepack, Csv or Json)");
     c.save_wavefns = to_bool(need("output.save_wavefns"), "output.save_wavefns");
     c.save_potential = to_bool(need("output.save_potential"), "output.save_potential");
     c.potential = enum_index(potential_names(), need("potential"), "potential");

@@ -29,8 +29,12 @@ struct Array3 {  // dense C-order array (x slowest, z contiguous)
 
 // ---------------------------------------------------------------- trilinear resize, input.rs:667-716
 // linspace follows ndarray 0.11: start + step * i with step = (end - start)/(n - 1)
-inline void trilerp_resize(const Array3& v, Array3& out) {
+// `basis`: number of points of the sampling basis per axis (linspace(0, n-1, basis)); the output takes its first
+// out.n* entries.  The reference's unit test calls it with basis == output size (input.rs:733-824); its loaders pass the
+// PADDED target size while filling the work area (input.rs:172, 651, 671-674), see embed_work.
+inline void trilerp_resize(const Array3& v, Array3& out, const size_t* basis = nullptr) {
     const size_t nx = v.nx - 1, ny = v.ny - 1, nz = v.nz - 1;
+    const size_t bx = basis ? basis[0] : out.nx, by = basis ? basis[1] : out.ny, bz = basis ? basis[2] : out.nz;
     auto lin = [](size_t n_hi, size_t n, size_t i) {
         const double step = n > 1 ? ((double)n_hi - 0.) / ((double)n - 1.) : 0.;
         return 0. + step * (double)i;
@@ -44,7 +48,7 @@ inline void trilerp_resize(const Array3& v, Array3& out) {
     for (size_t x = 0; x < out.nx; ++x)
         for (size_t y = 0; y < out.ny; ++y)
             for (size_t z = 0; z < out.nz; ++z) {
-                const double xl = lin(nx, out.nx, x), yl = lin(ny, out.ny, y), zl = lin(nz, out.nz, z);
+                const double xl = lin(nx, bx, x), yl = lin(ny, by, y), zl = lin(nz, bz, z);
                 size_t x0, x1, y0, y1, z0, z1;
                 bracket(nx, xl, x0, x1);
                 bracket(ny, yl, y0, y1);
@@ -236,7 +240,7 @@ inline void write_array(const std::string& stem, int file_type, const Array3& a)
     }
 }
 // input.rs:32-111 / 513-578: prefer the configured file type, then whichever of mpk / csv / json exists
-inline bool read_array(const std::string& stem, int preferred, Array3& out) {
+inline bool read_array(const std::string& stem, int preferred, Array3& out, int* used_type = nullptr) {
     auto exists = [](const std::string& p) { std::ifstream f(p); return (bool)f; };
     const int order[4] = {preferred, 0, 1, 2};
     for (int t : order) {
@@ -244,21 +248,35 @@ inline bool read_array(const std::string& stem, int preferred, Array3& out) {
         const std::string path = stem + extension(t);
         if (!exists(path)) continue;
         out = t == 0 ? read_mpk(path) : (t == 1 ? read_csv(path) : read_json(path));
+        if (used_type) *used_type = t;
         return true;
     }
     return false;
 }
 
-// fill_data (input.rs:149-176): embed a WORK-sized array into the padded one, resizing when the shapes differ
-inline void embed_work(const Array3& src, std::vector<double>& padded, size_t nx, size_t ny, size_t nz, size_t e) {
+// fill_data (input.rs:149-176) / read_csv (input.rs:641-657): embed the array of a file into the padded one.
+// Reproduced as the reference does it, quirks included:
+//   * the "same size" test compares the file's dims with the PADDED target.  csv files count their own dims + 2e
+//     (input.rs:641), so a work-sized csv is copied straight in; Messagepack / Json files of the work size are NOT "same"
+//     and go through the interpolation below even at equal resolution (a file of exactly the padded size would make the
+//     reference panic on a shape mismatch: an error here);
+//   * the interpolation basis has PADDED-size many points per axis, of which the work area takes the first n
+//     (input.rs:172 passes target_size): the data is squeezed by (n-1)/(n+2e-1) towards index 0.
+inline void embed_work(const Array3& src, std::vector<double>& padded, size_t nx, size_t ny, size_t nz, size_t e,
+                       bool from_csv = false) {
     const size_t py = ny + 2 * e, pz = nz + 2 * e;
     std::fill(padded.begin(), padded.end(), 0.0);
     const Array3* use = &src;
     Array3 resized;
-    if (src.nx != nx || src.ny != ny || src.nz != nz) {
+    const size_t bb = 2 * e, off = from_csv ? bb : 0;
+    const bool same = src.nx + off == nx + bb && src.ny + off == ny + bb && src.nz + off == nz + bb;
+    if (same && !from_csv)
+        throw std::runtime_error("input array already has the padded size: the reference's fill_data cannot load it (input.rs:167-169)");
+    if (!same) {
         resized.nx = nx; resized.ny = ny; resized.nz = nz;
         resized.data.assign(nx * ny * nz, 0.0);
-        trilerp_resize(src, resized);
+        const size_t basis[3] = {nx + bb, ny + bb, nz + bb};
+        trilerp_resize(src, resized, basis);
         use = &resized;
     }
     for (size_t i = 0; i < nx; ++i)

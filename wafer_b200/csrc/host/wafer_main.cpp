@@ -54,11 +54,10 @@ void write_work(const std::string& stem, int file_type, const double* padded, co
 }
 bool read_work(const std::string& stem, int file_type, std::vector<double>& padded, const Dims& d) {
     Array3 a;
-    if (!read_array(stem, file_type, a)) return false;
-    if (a.nx < 2 || a.ny < 2 || a.nz < 2) {
-        if (a.nx != d.nx || a.ny != d.ny || a.nz != d.nz) throw std::runtime_error("ArrayShape: " + stem + " cannot be resized");
-    }
-    embed_work(a, padded, d.nx, d.ny, d.nz, d.e);
+    int used = 0;
+    if (!read_array(stem, file_type, a, &used)) return false;
+    if (a.nx < 2 || a.ny < 2 || a.nz < 2) throw std::runtime_error("ArrayShape: " + stem + " cannot be resized");
+    embed_work(a, padded, d.nx, d.ny, d.nz, d.e, used == 1);
     return true;
 }
 
@@ -302,8 +301,17 @@ int main(int argc, char** argv) {
                 }
             }
             std::vector<double> padded(5 * 6 * 7);
-            embed_work(v, padded, 3, 4, 5, 1);
+            embed_work(v, padded, 3, 4, 5, 1, /*from_csv=*/true);  // a work-sized csv is copied straight in (input.rs:641-650)
             if (extract_work(padded.data(), 3, 4, 5, 1).data != v.data) return 1;
+            // a work-sized Messagepack / Json array is NOT "same" for the reference (input.rs:161-172): it is re-sampled
+            // on a basis of padded-size many points; check the first axis against the formula
+            embed_work(v, padded, 3, 4, 5, 1, false);
+            {
+                const Array3 w = extract_work(padded.data(), 3, 4, 5, 1);
+                const double xl = 2.0 / 4.0;  // linspace(0, 2, 5)[1]
+                const double want = v.at(0, 0, 0) * (1. - xl) + v.at(1, 0, 0) * xl;
+                if (std::fabs(w.at(1, 0, 0) - want) > 1e-15 * std::fabs(want) || w.at(0, 0, 0) != v.at(0, 0, 0)) return 1;
+            }
             puts("formats ok");
             return 0;
         }
