@@ -35,7 +35,7 @@ pub fn run(config: &Config, log: &Logger, debug_level: usize) -> Result<()> {
     Ok(())
 }
 
-fn solve(config: &Config, log: &Logger, _debug_level: usize, gpu: &Gpu, wnum: u8) -> Result<()> {
+fn solve(config: &Config, log: &Logger, debug_level: usize, gpu: &Gpu, wnum: u8) -> Result<()> {
     let num = &config.grid.size;
     let bb = config.central_difference.bb();
     let init_size: [usize; 3] = [num.x + bb, num.y + bb, num.z + bb];
@@ -77,8 +77,9 @@ fn solve(config: &Config, log: &Logger, _debug_level: usize, gpu: &Gpu, wnum: u8
             }
         }
         let diff = (norm_energy - last_energy).abs();
-        println!("{}", output::print_measurements(tau, r64(diff), &observables));
         if diff < config.tolerance.raw() {
+            // grid.rs:162-167: the row is printed at convergence only; between checks it goes to the progress bar
+            println!("{}", output::print_measurements(tau, r64(diff), &observables));
             output::finalise_measurement(&observables, wnum, r64(num.x as f64), &config.project_name,
                                          &config.output.file_type)?;
             if config.output.snap_update.is_some() {
@@ -88,6 +89,10 @@ fn solve(config: &Config, log: &Logger, _debug_level: usize, gpu: &Gpu, wnum: u8
             break;
         } else {
             last_energy = norm_energy;
+        }
+        if debug_level == 3 {
+            // grid.rs:198-209 (the ETA estimate of grid.rs:254-283 is unchanged and omitted here)
+            info!(log, "{}", output::print_measurements(tau, r64(diff), &observables));
         }
         if config.max_steps.is_some() && step > config.max_steps.unwrap() {
             break;

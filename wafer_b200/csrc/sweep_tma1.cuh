@@ -107,6 +107,21 @@ __device__ __forceinline__ void iteration(Smem<E>& sm, double2 (&q)[2][Cfg<E>::N
     using M = Mode<MODE>;
     constexpr int BW = C::BW;
     const int s_new = t % C::NST;
+    // the stored states at this iteration's output sites: issued before the wait on the TMA stage and the stencil
+    // arithmetic, consumed after them (loading them at the point of use left the whole DRAM latency exposed: the k = 1
+    // sweep took 1.0 ms against 0.6 ms for the plain one at 512^3, ncu r2n)
+    constexpr int NQ = (M::nred > 1 && !M::obs && !M::chk) ? M::nred - 1 : 0;
+    constexpr bool PREFETCH = E == 1 && NQ > 0 && NQ <= 2;  // anything more spills at the 128-register cap (ptxas -v)
+    double2 ql[2][NQ > 0 ? NQ : 1];
+    if (PREFETCH && t >= 2 * E) {
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+            if (tl.yin[s] && ln.st0) {
+#pragma unroll
+                for (int i = 0; i < NQ; ++i)
+                    ql[s][i] = __ldg(reinterpret_cast<const double2*>(ex.q[i] + ((orow - out_base) + s * row_pitch)));
+            }
+    }
     tb::mbar_wait(&sm.full[s_new], (t / C::NST) & 1);
     const double* psn = sm.st[s_new].psi + ln.cb;
 #pragma unroll
@@ -206,8 +221,8 @@ __device__ __forceinline__ void iteration(Smem<E>& sm, double2 (&q)[2][Cfg<E>::N
                         if (M::nred >= 1) acc[0] = D_ADD(acc[0], D_ADD(D_MUL(r.x, r.x), D_MUL(r.y, r.y)));
 #pragma unroll
                         for (int i = 1; i < M::nred; ++i) {  // the stored states share psi's layout: same element offset
-                            const double2 ql = __ldg(reinterpret_cast<const double2*>(ex.q[i - 1] + ((orow - out_base) + s * row_pitch)));
-                            acc[i] = D_ADD(acc[i], D_ADD(D_MUL(ql.x, r.x), D_MUL(ql.y, r.y)));
+                            if (!PREFETCH) ql[s][i - 1] = __ldg(reinterpret_cast<const double2*>(ex.q[i - 1] + ((orow - out_base) + s * row_pitch)));
+                            acc[i] = D_ADD(acc[i], D_ADD(D_MUL(ql[s][i - 1].x, r.x), D_MUL(ql[s][i - 1].y, r.y)));
                         }
                     }
                 }
