@@ -16,6 +16,11 @@ run_check() {  # name, env...
 run_check p2p WAFER_P2P=1
 [ "${SKIP_NEG:-0}" = 1 ] || run_check p2p_nofinalwait WAFER_P2P=1 WAFER_DEBUG_SKIP_FINAL_WAIT=1   # must FAIL: proves the drift test sees the race
 run_check nccl WAFER_P2P=0
+if [ "${EXCITED:-1}" = 1 ]; then
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29555 \
+      scripts/multigpu_excited.py > "$OUT/excited_$N.log" 2>&1
+  echo "excited rc=$?" | tee -a "$OUT/rc.log"; grep '^{' "$OUT/excited_$N.log" | tail -1
+fi
 for n in ${NLIST:-$N}; do
   if [ $n -eq 1 ]; then
     timeout 900 python bench.py --gpus 1 --steps 3 --warmup 3 --no-cpu --no-512 $EXTRA > "$OUT/scale_$n.json" 2> "$OUT/scale_$n.err"

@@ -12,6 +12,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <new>
+#include <stdexcept>
 #include <string>
 #include <utility>
 #include <vector>
@@ -918,8 +920,15 @@ const char* wafer_version(void) { return "wafer_b200 0.1 (sm_100a)"; }
 int wafer_create(const wafer_params* params, wafer_ctx** out) {
     if (!params || !out) { g_create_error = "NULL argument"; return WAFER_ERR_INVALID; }
     *out = nullptr;
-    wafer_ctx* ctx = new wafer_ctx();
-    const int rc = create_impl(params, ctx);
+    wafer_ctx* ctx = new (std::nothrow) wafer_ctx();
+    if (!ctx) { g_create_error = "out of host memory"; return WAFER_ERR_INVALID; }
+    int rc;
+    try {
+        rc = create_impl(params, ctx);
+    } catch (const std::exception& e) {
+        ctx->err = std::string("wafer_create: ") + e.what();
+        rc = WAFER_ERR_INVALID;
+    }
     if (rc != WAFER_OK) {
         g_create_error = ctx->err;
         wafer_destroy(ctx);
@@ -1094,7 +1103,7 @@ int wafer_get_phi_slab(wafer_ctx* ctx, double* chunk) {
     return download(ctx, ctx->psi[ctx->cur], chunk, hp0, hp0, hp1);
 }
 
-int wafer_push_lower(wafer_ctx* ctx, const double* q_padded) {
+static int wafer_push_lower_impl(wafer_ctx* ctx, const double* q_padded) {
     if (!ctx) return WAFER_ERR_INVALID;
     REQUIRE(q_padded, "q_padded is NULL");
     REQUIRE(ctx->lowers.size() < 255, "at most 255 lower states (wavenum is a u8, config.rs:308)");
@@ -1107,7 +1116,7 @@ int wafer_push_lower(wafer_ctx* ctx, const double* q_padded) {
     return rc;
 }
 
-int wafer_push_lower_from_phi(wafer_ctx* ctx) {
+static int wafer_push_lower_from_phi_impl(wafer_ctx* ctx) {
     if (!ctx) return WAFER_ERR_INVALID;
     if (!ctx->have_phi) { ctx->err = "phi not set"; return WAFER_ERR_NOT_READY; }
     REQUIRE(ctx->lowers.size() < 255, "at most 255 lower states (wavenum is a u8, config.rs:308)");
@@ -1242,7 +1251,7 @@ int wafer_orthogonalise(wafer_ctx* ctx, uint8_t wnum) {
     return gs_apply(ctx, ctx->psi[ctx->cur], nullptr, n);
 }
 
-int wafer_evolve(wafer_ctx* ctx, uint8_t wnum_in, uint64_t steps) {
+static int wafer_evolve_impl(wafer_ctx* ctx, uint8_t wnum_in, uint64_t steps) {
     if (!ctx) return WAFER_ERR_INVALID;
     TRY(ready(ctx, true));
     CK(cudaSetDevice(ctx->dev));
@@ -1353,6 +1362,33 @@ int wafer_evolve(wafer_ctx* ctx, uint8_t wnum_in, uint64_t steps) {
         ctx->chk_valid = true;
     }
     return WAFER_OK;
+}
+
+int wafer_push_lower(wafer_ctx* ctx, const double* q_padded) {
+    try {
+        return wafer_push_lower_impl(ctx, q_padded);
+    } catch (const std::exception& e) {  // host-side allocation failures must not unwind through the C ABI
+        if (ctx) ctx->err = std::string("wafer_push_lower: ") + e.what();
+        return WAFER_ERR_INVALID;
+    }
+}
+
+int wafer_push_lower_from_phi(wafer_ctx* ctx) {
+    try {
+        return wafer_push_lower_from_phi_impl(ctx);
+    } catch (const std::exception& e) {  // host-side allocation failures must not unwind through the C ABI
+        if (ctx) ctx->err = std::string("wafer_push_lower_from_phi: ") + e.what();
+        return WAFER_ERR_INVALID;
+    }
+}
+
+int wafer_evolve(wafer_ctx* ctx, uint8_t wnum_in, uint64_t steps) {
+    try {
+        return wafer_evolve_impl(ctx, wnum_in, steps);
+    } catch (const std::exception& e) {  // host-side allocation failures must not unwind through the C ABI
+        if (ctx) ctx->err = std::string("wafer_evolve: ") + e.what();
+        return WAFER_ERR_INVALID;
+    }
 }
 
 int wafer_check(wafer_ctx* ctx, uint8_t wnum_in, wafer_observables* out) {
