@@ -19,6 +19,10 @@
 #include "kernels.cuh"
 #include "sweep_tb.cuh"
 
+#ifndef WAFER_T1_NPRE3
+#define WAFER_T1_NPRE3 2
+#endif
+
 namespace wafer {
 namespace t1 {
 
@@ -111,14 +115,15 @@ __device__ __forceinline__ void iteration(Smem<E>& sm, double2 (&q)[2][Cfg<E>::N
     // arithmetic, consumed after them (loading them at the point of use left the whole DRAM latency exposed: the k = 1
     // sweep took 1.0 ms against 0.6 ms for the plain one at 512^3, ncu r2n)
     constexpr int NQ = (M::nred > 1 && !M::obs && !M::chk) ? M::nred - 1 : 0;
-    constexpr bool PREFETCH = E == 1 && NQ > 0 && NQ <= 2;  // anything more spills at the 128-register cap (ptxas -v)
+    // NPRE of the NQ states are fetched early; more than that spills at the 128-register cap (ptxas -v)
+    constexpr int NPRE = E != 1 ? 0 : (NQ <= 2 ? NQ : WAFER_T1_NPRE3);
     double2 ql[2][NQ > 0 ? NQ : 1];
-    if (PREFETCH && t >= 2 * E) {
+    if (NPRE > 0 && t >= 2 * E) {
 #pragma unroll
         for (int s = 0; s < 2; ++s)
             if (tl.yin[s] && ln.st0) {
 #pragma unroll
-                for (int i = 0; i < NQ; ++i)
+                for (int i = 0; i < NPRE; ++i)
                     ql[s][i] = __ldg(reinterpret_cast<const double2*>(ex.q[i] + ((orow - out_base) + s * row_pitch)));
             }
     }
@@ -221,7 +226,7 @@ __device__ __forceinline__ void iteration(Smem<E>& sm, double2 (&q)[2][Cfg<E>::N
                         if (M::nred >= 1) acc[0] = D_ADD(acc[0], D_ADD(D_MUL(r.x, r.x), D_MUL(r.y, r.y)));
 #pragma unroll
                         for (int i = 1; i < M::nred; ++i) {  // the stored states share psi's layout: same element offset
-                            if (!PREFETCH) ql[s][i - 1] = __ldg(reinterpret_cast<const double2*>(ex.q[i - 1] + ((orow - out_base) + s * row_pitch)));
+                            if (i - 1 >= NPRE) ql[s][i - 1] = __ldg(reinterpret_cast<const double2*>(ex.q[i - 1] + ((orow - out_base) + s * row_pitch)));
                             acc[i] = D_ADD(acc[i], D_ADD(D_MUL(ql[s][i - 1].x, r.x), D_MUL(ql[s][i - 1].y, r.y)));
                         }
                     }
