@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -366,22 +367,29 @@ int tb2_schedule(wafer_ctx* ctx, int xb, int xe, const Tb2Sched** out) {
     return WAFER_OK;
 }
 
-// two lattice steps: psi[src] -> psi[src^1] for planes [xb, xe); peer != nullptr: also store every output at the
-// same (plane + peer_plane_shift, row, column) of the neighbour's buffer `peer`
-int launch_sweep_tb2(wafer_ctx* ctx, int src, int xb, int xe, cudaStream_t st, double* peer = nullptr,
-                     long long peer_plane_shift = 0) {
+// two lattice steps: psi[src] -> psi[src^1] for planes [xb, xe).  peer_lo / peer_hi != nullptr: the output planes
+// [xb, lo_end) / [hi_begin, xe) are also stored into the lower / upper neighbour's buffer, at plane + shift_lo / shift_hi.
+struct PeerTargets {
+    double* lo = nullptr;
+    double* hi = nullptr;
+    long long shift_lo = 0, shift_hi = 0;
+    int lo_end = INT_MIN, hi_begin = INT_MAX;
+};
+int launch_sweep_tb2(wafer_ctx* ctx, int src, int xb, int xe, cudaStream_t st, const PeerTargets* pt = nullptr) {
     if (xe <= xb) return WAFER_OK;
     const Geom& g = ctx->g;
     const Tb2Sched* sc = nullptr;
     TRY(tb2_schedule(ctx, xb, xe, &sc));
     double* out = ctx->psi[src ^ 1];
     const tb::Sched ks{sc->bulk, sc->nbulk, sc->segs, sc->first, sc->counters};
-    if (peer) {
-        const long long delta = (peer - out) + peer_plane_shift * g.plane;  // element distance local site -> peer site
-        tb::sweep_tb2_kernel<true><<<sc->ncta, tb::THREADS, tb::SMEM_BYTES, st>>>(ctx->tm_psi[src], ctx->tm_v, out, delta, g, ks,
+    if (pt && (pt->lo || pt->hi)) {
+        tb::PeerStores pr{0, 0, INT_MIN, INT_MAX};
+        if (pt->lo) { pr.delta_lo = (pt->lo - out) + pt->shift_lo * g.plane; pr.lo_end = pt->lo_end; }
+        if (pt->hi) { pr.delta_hi = (pt->hi - out) + pt->shift_hi * g.plane; pr.hi_begin = pt->hi_begin; }
+        tb::sweep_tb2_kernel<true><<<sc->ncta, tb::THREADS, tb::SMEM_BYTES, st>>>(ctx->tm_psi[src], ctx->tm_v, out, pr, g, ks,
                                                                                   ctx->p.dt, denominator(ctx), ctx->den_ok);
     } else {
-        tb::sweep_tb2_kernel<false><<<sc->ncta, tb::THREADS, tb::SMEM_BYTES, st>>>(ctx->tm_psi[src], ctx->tm_v, out, 0, g, ks,
+        tb::sweep_tb2_kernel<false><<<sc->ncta, tb::THREADS, tb::SMEM_BYTES, st>>>(ctx->tm_psi[src], ctx->tm_v, out, tb::PeerStores{}, g, ks,
                                                                                    ctx->p.dt, denominator(ctx), ctx->den_ok);
     }
     return post_launch(ctx);
@@ -1285,7 +1293,33 @@ static int wafer_evolve_impl(wafer_ctx* ctx, uint8_t wnum_in, uint64_t steps) {
         const int src = ctx->cur;
         const double* cur = ctx->psi[src];
         double* nxt = ctx->psi[src ^ 1];
-        if (overlap) {
+        // Fused halos, two-step pass, "whole column" form (default): ONE launch on the main stream sweeps all owned planes and
+        // stores its first / last two output planes into the neighbours' ghost planes as it produces them; the neighbours'
+        // pass counters are awaited before it and published after it.  No separate boundary launches: those produce 2 planes
+        // for 6 plane-iterations of pipeline (140 instead of 132 iterations per tile column at 128 planes per rank, and four
+        // small launches that the persistent interior kernel serialises behind itself anyway — 0.894 parallel efficiency at
+        // N = 8, profiles/scaling_r2).  The price is a per-pass handshake between neighbours instead of a pass of slack.
+        static const bool split_halo = getenv("WAFER_P2P_SPLIT") && atoi(getenv("WAFER_P2P_SPLIT")) == 1;
+        if (fused && two && !split_halo) {
+            CK(cudaStreamWaitEvent(ctx->s_main, ctx->ev_halo, 0));  // an earlier pass may have used the halo stream
+            if (ctx->dbg_halo_delay_ns) {
+                spin_kernel<<<1, 1, 0, ctx->s_main>>>(ctx->dbg_halo_delay_ns);
+                TRY(post_launch(ctx));
+            }
+            // counter >= P: the neighbours have finished pass P-1 — their stores into my ghost planes of `cur` have landed,
+            // and they no longer read the ghost planes (of their `nxt`) that this pass overwrites
+            p2p_wait_kernel<<<1, 1, 0, ctx->s_main>>>(ctx->flags, ctx->pass, has_lo, has_hi, ctx->p2p_timeout);
+            TRY(post_launch(ctx));
+            PeerTargets pt;
+            if (has_lo) { pt.lo = ctx->peer_psi[0][src ^ 1]; pt.shift_lo = ctx->peer_L[0]; pt.lo_end = b; }
+            if (has_hi) { pt.hi = ctx->peer_psi[1][src ^ 1]; pt.shift_hi = -(long long)g.L; pt.hi_begin = g.L - b; }
+            TRY(launch_sweep_tb2(ctx, src, 0, g.L, ctx->s_main, &pt));
+            ctx->pass += 1;
+            p2p_signal_kernel<<<1, 1, 0, ctx->s_main>>>(has_lo ? ctx->peer_flags[0] : nullptr, has_hi ? ctx->peer_flags[1] : nullptr, ctx->pass);
+            TRY(post_launch(ctx));
+            CK(cudaEventRecord(ctx->ev_main, ctx->s_main));
+            CK(cudaEventRecord(ctx->ev_halo, ctx->s_main));
+        } else if (overlap) {
             // boundary planes + halo on the high-priority stream, interior on the main stream
             CK(cudaStreamWaitEvent(ctx->s_halo, ctx->ev_main, 0));
             CK(cudaStreamWaitEvent(ctx->s_main, ctx->ev_halo, 0));
@@ -1303,8 +1337,11 @@ static int wafer_evolve_impl(wafer_ctx* ctx, uint8_t wnum_in, uint64_t steps) {
             double* phi_ = fused && has_hi ? ctx->peer_psi[1][src ^ 1] : nullptr;
             if (two) {
                 // my planes [0,b) are the lower neighbour's ghost planes [L_lo, L_lo+b); my [L-b,L) the upper one's [-b,0)
-                TRY(launch_sweep_tb2(ctx, src, 0, b, ctx->s_halo, plo, ctx->peer_L[0]));
-                TRY(launch_sweep_tb2(ctx, src, g.L - b, g.L, ctx->s_halo, phi_, -(long long)g.L));
+                PeerTargets lo_t, hi_t;
+                if (plo) { lo_t.lo = plo; lo_t.shift_lo = ctx->peer_L[0]; lo_t.lo_end = b; }
+                if (phi_) { hi_t.hi = phi_; hi_t.shift_hi = -(long long)g.L; hi_t.hi_begin = g.L - b; }
+                TRY(launch_sweep_tb2(ctx, src, 0, b, ctx->s_halo, &lo_t));
+                TRY(launch_sweep_tb2(ctx, src, g.L - b, g.L, ctx->s_halo, &hi_t));
             } else {
                 // (final step with fused check sums: the three launches share one row of per-CTA partial sums)
                 const int nb_lo = sweep_blocks(ctx, 0, b), nb_hi = sweep_blocks(ctx, g.L - b, g.L);
