@@ -13,7 +13,7 @@ from . import _capi
 from ._capi import Observables, Params, Record
 
 __all__ = ["Lattice", "slab_partition", "WaferError", "POTENTIALS", "INITIAL_CONDITIONS", "EXT", "nccl_unique_id", "pinned_empty",
-           "FLAG_AB_ARRAYS"]
+           "pin", "unpin", "FLAG_AB_ARRAYS"]
 
 # PotentialType (config.rs:74-104), InitialCondition (config.rs:153-170), CentralDifference.ext() (config.rs:232-238)
 POTENTIALS = {
@@ -76,6 +76,18 @@ _PINNED = {}
 def pinned_free(arr):
     """Release a pinned_empty() array; the array (and every view of it) must not be used afterwards."""
     _capi.load().wafer_host_free(_PINNED.pop(arr.ctypes.data))
+
+
+def pin(arr):
+    """page-lock an existing C-contiguous float64 array in place (wafer_host_register); undo with unpin()"""
+    rc = _capi.load().wafer_host_register(arr.ctypes.data_as(C.c_void_p), arr.nbytes)
+    if rc:
+        raise WaferError(rc, "wafer_host_register(%d bytes) failed" % arr.nbytes)
+    return arr
+
+
+def unpin(arr):
+    _capi.load().wafer_host_unregister(arr.ctypes.data_as(C.c_void_p))
 
 
 def _p(a):

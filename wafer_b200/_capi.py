@@ -67,6 +67,8 @@ SYMBOLS = {
     "wafer_kernel_launches": (C.c_uint64, [_ctx]),
     "wafer_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "wafer_host_free": (C.c_int, [C.c_void_p]),
+    "wafer_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "wafer_host_unregister": (C.c_int, [C.c_void_p]),
     "wafer_device_info": (C.c_int, [_ctx, C.c_char_p, C.c_size_t, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                     C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]),
     "wafer_p2p_export": (C.c_int, [_ctx, C.POINTER(C.c_uint8)]),

@@ -1519,6 +1519,13 @@ int wafer_host_alloc(void** ptr, size_t bytes) {
 
 int wafer_host_free(void* ptr) { return cudaFreeHost(ptr) == cudaSuccess ? WAFER_OK : WAFER_ERR_CUDA; }
 
+int wafer_host_register(void* ptr, size_t bytes) {
+    if (!ptr || !bytes) return WAFER_ERR_INVALID;
+    return cudaHostRegister(ptr, bytes, cudaHostRegisterDefault) == cudaSuccess ? WAFER_OK : WAFER_ERR_CUDA;
+}
+
+int wafer_host_unregister(void* ptr) { return cudaHostUnregister(ptr) == cudaSuccess ? WAFER_OK : WAFER_ERR_CUDA; }
+
 int wafer_device_info(const wafer_ctx* ctx, char* name, size_t name_len, int32_t* sm_count, int32_t* cc_major,
                       int32_t* cc_minor, uint64_t* mem_bytes) {
     if (!ctx) return WAFER_ERR_INVALID;
