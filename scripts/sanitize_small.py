@@ -27,4 +27,22 @@ for cd, ext, shape in (("ThreePoint", 1, (37, 33, 70)), ("FivePoint", 2, (12, 9,
         lat.generate_potential("Harmonic")
         lat.set_initial_conditions("Boolean")
         lat.solve(0, 1e-3, max_steps=20, screen_update=4)
+        if ext == 1:
+            # round 2: a multi-segment persistent launch (several tile columns per CTA would need a big lattice; a tall thin
+            # one gives every CTA bulk + tail segments), the fused check sums (>= 64 steps), more stored states than one pass
+            lat.evolve(0, 66)
+            lat.check(0)
+            for _ in range(4):
+                lat.push_lower()
+            lat.phi_seed_from_lower(0)
+            lat.evolve(5, 2)
+            lat.check(5)
+            lat.phi_checksum()
+            lat.set_phi_owned(lat.get_phi_slab())
+# many tile columns on few planes: the in-order dispatcher hands out bulk items and static tail shares
+with wafer_b200.Lattice((24, 400, 500), "ThreePoint", dn=0.1, dt=2e-3, mass=1.0) as lat:
+    lat.generate_potential("Harmonic")
+    lat.set_initial_conditions("Boolean")
+    lat.evolve(0, 4)
+    lat.check(0)
 print("sanitize run complete")
