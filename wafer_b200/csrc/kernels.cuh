@@ -430,6 +430,13 @@ __global__ void __launch_bounds__(EW_THREADS)
     block_reduce_store<1>(acc, partials, gridDim.x, blockIdx.x);
 }
 
+// h = (dt*v)/2 over a whole slab buffer: the first two operations of potential.rs:104-110, taken out of the time-tiled sweep
+__global__ void __launch_bounds__(EW_THREADS)
+    build_h_kernel(const double* __restrict__ v, double* __restrict__ h, long long n, double dt) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) h[i] = D_MUL(D_MUL(dt, v[i]), 0.5);
+}
+
 // A,B arrays from V over a whole slab buffer (potential.rs:104-110)
 __global__ void __launch_bounds__(EW_THREADS)
     build_ab_kernel(const double* __restrict__ v, double* __restrict__ a, double* __restrict__ b, long long n, double dt) {

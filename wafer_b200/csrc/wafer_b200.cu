@@ -51,6 +51,9 @@ struct wafer_ctx {
     bool onfly = true;
     bool use_tb = false;            // time-tiled TMA sweep available (ThreePoint, V on the fly)
     CUtensorMap tm_psi[2], tm_v;    // TMA descriptors of the interior of psi[0], psi[1], v
+    double* hfield = nullptr;       // h = (dt*v)/2 for the time-tiled sweep (WAFER_TB_HFIELD), rebuilt when V changes
+    CUtensorMap tm_h;
+    bool h_valid = false;
     int den_ok = 0;
     std::map<std::pair<int, int>, Tb2Sched> tb2_sched;  // keyed by the plane range [xb, xe)
     bool use_t1 = false;            // TMA-pipelined one-step sweep (WAFER_FLAG_TMA_ONE_STEP)
@@ -237,8 +240,10 @@ int init_tb(wafer_ctx* ctx) {
     TRY(make_tensor_map(ctx, &ctx->tm_psi[0], ctx->psi[0], tb::R0));
     TRY(make_tensor_map(ctx, &ctx->tm_psi[1], ctx->psi[1], tb::R0));
     TRY(make_tensor_map(ctx, &ctx->tm_v, ctx->v, tb::R1));
-    CK(cudaFuncSetAttribute(tb::sweep_tb2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb::SMEM_BYTES));
-    CK(cudaFuncSetAttribute(tb::sweep_tb2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(tb::sweep_tb2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(tb::sweep_tb2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(tb::sweep_tb2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(tb::sweep_tb2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb::SMEM_BYTES));
     const double den = denominator(ctx);
     ctx->den_ok = (den > 7.888609052210118e-31 && den < 1.2676506002282294e30) ? 1 : 0;  // 2^-100 .. 2^100
     ctx->use_tb = true;
@@ -375,9 +380,26 @@ struct PeerTargets {
     long long shift_lo = 0, shift_hi = 0;
     int lo_end = INT_MIN, hi_begin = INT_MAX;
 };
+// The time-tiled sweep can read h = (dt*v)/2 instead of V: same bytes, two DMULs less per site and sweep pair, at the price
+// of one more field in HBM.  Built lazily on the main stream; every launch of the sweep is ordered after it there.
+int ensure_hfield(wafer_ctx* ctx) {
+    static const bool want = !(getenv("WAFER_TB_HFIELD") && atoi(getenv("WAFER_TB_HFIELD")) == 0);
+    if (!want || ctx->h_valid) return WAFER_OK;
+    if (!ctx->hfield) {
+        if (cudaMalloc(&ctx->hfield, ctx->bytes()) != cudaSuccess) { cudaGetLastError(); ctx->hfield = nullptr; return WAFER_OK; }  // no room: keep V
+        TRY(make_tensor_map(ctx, &ctx->tm_h, ctx->hfield, tb::R1));
+    }
+    const long long n = ctx->g.total();
+    build_h_kernel<<<ew_grid(ctx, n), EW_THREADS, 0, ctx->s_main>>>(ctx->v, ctx->hfield, n, ctx->p.dt);
+    TRY(post_launch(ctx));
+    ctx->h_valid = true;
+    return WAFER_OK;
+}
+
 int launch_sweep_tb2(wafer_ctx* ctx, int src, int xb, int xe, cudaStream_t st, const PeerTargets* pt = nullptr) {
     if (xe <= xb) return WAFER_OK;
     const Geom& g = ctx->g;
+    const bool hf = ctx->h_valid;
     const Tb2Sched* sc = nullptr;
     TRY(tb2_schedule(ctx, xb, xe, &sc));
     double* out = ctx->psi[src ^ 1];
@@ -386,11 +408,12 @@ int launch_sweep_tb2(wafer_ctx* ctx, int src, int xb, int xe, cudaStream_t st, c
         tb::PeerStores pr{0, 0, INT_MIN, INT_MAX};
         if (pt->lo) { pr.delta_lo = (pt->lo - out) + pt->shift_lo * g.plane; pr.lo_end = pt->lo_end; }
         if (pt->hi) { pr.delta_hi = (pt->hi - out) + pt->shift_hi * g.plane; pr.hi_begin = pt->hi_begin; }
-        tb::sweep_tb2_kernel<true><<<sc->ncta, tb::THREADS, tb::SMEM_BYTES, st>>>(ctx->tm_psi[src], ctx->tm_v, out, pr, g, ks,
-                                                                                  ctx->p.dt, denominator(ctx), ctx->den_ok);
+        if (hf) tb::sweep_tb2_kernel<true, true><<<sc->ncta, tb::THREADS, tb::SMEM_BYTES, st>>>(ctx->tm_psi[src], ctx->tm_h, out, pr, g, ks, ctx->p.dt, denominator(ctx), ctx->den_ok);
+        else tb::sweep_tb2_kernel<true, false><<<sc->ncta, tb::THREADS, tb::SMEM_BYTES, st>>>(ctx->tm_psi[src], ctx->tm_v, out, pr, g, ks, ctx->p.dt, denominator(ctx), ctx->den_ok);
     } else {
-        tb::sweep_tb2_kernel<false><<<sc->ncta, tb::THREADS, tb::SMEM_BYTES, st>>>(ctx->tm_psi[src], ctx->tm_v, out, tb::PeerStores{}, g, ks,
-                                                                                   ctx->p.dt, denominator(ctx), ctx->den_ok);
+        const tb::PeerStores none{};
+        if (hf) tb::sweep_tb2_kernel<false, true><<<sc->ncta, tb::THREADS, tb::SMEM_BYTES, st>>>(ctx->tm_psi[src], ctx->tm_h, out, none, g, ks, ctx->p.dt, denominator(ctx), ctx->den_ok);
+        else tb::sweep_tb2_kernel<false, false><<<sc->ncta, tb::THREADS, tb::SMEM_BYTES, st>>>(ctx->tm_psi[src], ctx->tm_v, out, none, g, ks, ctx->p.dt, denominator(ctx), ctx->den_ok);
     }
     return post_launch(ctx);
 }
@@ -958,6 +981,7 @@ int wafer_destroy(wafer_ctx* ctx) {
     }
     cudaFree(ctx->flags); cudaFree(ctx->p2p_timeout);
     for (double* q : ctx->lowers) cudaFree(q);
+    cudaFree(ctx->hfield);
     cudaFree(ctx->psi[0]); cudaFree(ctx->psi[1]); cudaFree(ctx->v); cudaFree(ctx->a); cudaFree(ctx->b);
     for (int b = 0; b < 2; ++b) {
         cudaFree(ctx->stg[b]);
@@ -1014,6 +1038,7 @@ int wafer_set_potential(wafer_ctx* ctx, const double* v_padded) {
     ctx->chk_valid = false;  // psi (or what the check sums depend on) changes
     REQUIRE(v_padded, "v_padded is NULL");
     CK(cudaSetDevice(ctx->dev));
+    ctx->h_valid = false;
     TRY(upload_global(ctx, v_padded, ctx->v, false, false));
     TRY(ensure_ab(ctx));
     ctx->have_v = true;
@@ -1185,6 +1210,7 @@ int wafer_generate_potential(wafer_ctx* ctx, int32_t kind, double sig) {
     GenParams gp = make_gen_params(ctx->p.dn, ctx->p.mass, sig);
     REQUIRE(potential_kind_supported(kind), "PotentialNotAvailable: no formula for this potential kind (potential.rs:315-317)");
     const long long rows = (long long)(ctx->g.L + 2 * ctx->g.gx) * ctx->g.ny;
+    ctx->h_valid = false;
     gen_potential_kernel<<<(int)std::min<long long>(rows, (long long)ctx->sm_count * 32), 128, 0, ctx->s_main>>>(ctx->v, ctx->g, kind, gp);
     TRY(post_launch(ctx));
     TRY(ensure_ab(ctx));
@@ -1269,6 +1295,8 @@ static int wafer_evolve_impl(wafer_ctx* ctx, uint8_t wnum_in, uint64_t steps) {
     // every rank must take the same branch (one side calling NCCL while the other stores through peer memory would
     // hang): decide from the smallest slab of the decomposition, not from this rank's own L
     const bool overlap = ctx->world > 1 && !excited && ctx->min_L > 2 * g.gx;
+    // (before the events below: the halo stream's launches must come after the build of h as well)
+    if (ctx->use_tb && !excited && steps >= 4) TRY(ensure_hfield(ctx));  // one 16 B/site pass: pays for itself after two sweep pairs
     if (overlap) {
         CK(cudaEventRecord(ctx->ev_main, ctx->s_main));
         CK(cudaEventRecord(ctx->ev_halo, ctx->s_main));
