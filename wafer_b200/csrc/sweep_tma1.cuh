@@ -95,6 +95,7 @@ struct Extra {
     const double* potsub_arr;           // pot_sub array in the slab layout (potential.rs:135-144), or NULL
     double potsub;                      // pot_sub scalar (potential.rs:148-152)
     int nb_total, bid_off;              // partial-sum row length / this launch's first column when several launches share a row
+    int hf;                             // sweep modes: the "V" tensor map describes h = (dt*v)/2 (wafer_b200.cu::ensure_hfield)
 };
 
 // cold path of the energy integrand: plain IEEE division (grid.rs:325-332)
@@ -200,14 +201,19 @@ __device__ __forceinline__ void iteration(Smem<E>& sm, double2 (&q)[2][Cfg<E>::N
                 }
             } else {
                 double a0, bd0, a1, bd1;
-                tb::ab_fast(vv.x, hdt, dt, a0, bd0, b0);
-                tb::ab_fast(vv.y, hdt, dt, a1, bd1, b1);
+                if (ex.hf) {  // (CTA-uniform) two DMULs less per site
+                    tb::ab_fast_h(vv.x, dt, a0, bd0, b0);
+                    tb::ab_fast_h(vv.y, dt, a1, bd1, b1);
+                } else {
+                    tb::ab_fast(vv.x, hdt, dt, a0, bd0, b0);
+                    tb::ab_fast(vv.y, hdt, dt, a1, bd1, b1);
+                }
                 double2 r;
                 r.x = tb::update_fast(w.x, a0, bd0, s0, dc, b0);
                 r.y = tb::update_fast(w.y, a1, bd1, s1, dc, b1);
                 if ((w0 && (b0 || nofast)) || (w1 && (b1 || nofast))) {  // cold: an operand left the fast-division window
-                    r.x = tb::site_safe(w.x, vv.x, s0, dt, dc.den).u;
-                    r.y = tb::site_safe(w.y, vv.y, s1, dt, dc.den).u;
+                    r.x = ex.hf ? tb::site_safe_h(w.x, vv.x, s0, dt, dc.den).u : tb::site_safe(w.x, vv.x, s0, dt, dc.den).u;
+                    r.y = ex.hf ? tb::site_safe_h(w.y, vv.y, s1, dt, dc.den).u : tb::site_safe(w.y, vv.y, s1, dt, dc.den).u;
                 }
                 if (w0) {
                     if (!w1) r.y = 0.0;  // odd nz: the pad column keeps its zero

@@ -57,7 +57,7 @@ struct wafer_ctx {
     int den_ok = 0;
     std::map<std::pair<int, int>, Tb2Sched> tb2_sched;  // keyed by the plane range [xb, xe)
     bool use_t1 = false;            // TMA-pipelined one-step sweep (WAFER_FLAG_TMA_ONE_STEP)
-    CUtensorMap t1_psi[2], t1_v;
+    CUtensorMap t1_psi[2], t1_v, t1_h;
     cudaStream_t s_main = nullptr, s_halo = nullptr;
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_main = nullptr, ev_halo = nullptr;
     double* psi[2] = {nullptr, nullptr};
@@ -388,6 +388,10 @@ int ensure_hfield(wafer_ctx* ctx) {
     if (!ctx->hfield) {
         if (cudaMalloc(&ctx->hfield, ctx->bytes()) != cudaSuccess) { cudaGetLastError(); ctx->hfield = nullptr; return WAFER_OK; }  // no room: keep V
         TRY(make_tensor_map(ctx, &ctx->tm_h, ctx->hfield, tb::R1));
+        if (ctx->use_t1) {
+            const int rows = ctx->p.ext == 1 ? t1::Cfg<1>::TY : (ctx->p.ext == 2 ? t1::Cfg<2>::TY : t1::Cfg<3>::TY);
+            TRY(make_tensor_map(ctx, &ctx->t1_h, ctx->hfield, rows));
+        }
     }
     const long long n = ctx->g.total();
     build_h_kernel<<<ew_grid(ctx, n), EW_THREADS, 0, ctx->s_main>>>(ctx->v, ctx->hfield, n, ctx->p.dt);
@@ -483,11 +487,14 @@ int launch_sweep_t1(wafer_ctx* ctx, int src, int xb, int xe, int mode, cudaStrea
     ex.potsub = ctx->potsub_scalar;
     ex.nb_total = nb_total;
     ex.bid_off = bid_off;
+    const bool sweep_mode = mode < t1::MODE_OBS || mode >= t1::MODE_CHK;
+    ex.hf = sweep_mode && ctx->h_valid ? 1 : 0;
+    const CUtensorMap& tmv = ex.hf ? ctx->t1_h : ctx->t1_v;
     // the observables modes read psi[src] and store nothing: `out` only anchors the element offsets
     double* out = (mode >= t1::MODE_OBS && mode < t1::MODE_CHK) ? ctx->psi[src] : ctx->psi[src ^ 1];
 #define T1_CASE(M)                                                                                                              \
     case M:                                                                                                                     \
-        t1::sweep_tma1_kernel<E, M><<<grid, t1::Cfg<E>::THREADS, smem, st>>>(ctx->t1_psi[src], ctx->t1_v, out, g, xb, xe, chunk,      \
+        t1::sweep_tma1_kernel<E, M><<<grid, t1::Cfg<E>::THREADS, smem, st>>>(ctx->t1_psi[src], tmv, out, g, xb, xe, chunk,           \
                                                                              ctx->p.dt, denominator(ctx), ctx->den_ok, ctx->partials, ex); \
         break;
     switch (mode) {
@@ -1296,7 +1303,7 @@ static int wafer_evolve_impl(wafer_ctx* ctx, uint8_t wnum_in, uint64_t steps) {
     // hang): decide from the smallest slab of the decomposition, not from this rank's own L
     const bool overlap = ctx->world > 1 && !excited && ctx->min_L > 2 * g.gx;
     // (before the events below: the halo stream's launches must come after the build of h as well)
-    if (ctx->use_tb && !excited && steps >= 4) TRY(ensure_hfield(ctx));  // one 16 B/site pass: pays for itself after two sweep pairs
+    if ((ctx->use_tb || ctx->use_t1) && steps >= 4) TRY(ensure_hfield(ctx));  // one 16 B/site pass: pays for itself within a few sweeps
     if (overlap) {
         CK(cudaEventRecord(ctx->ev_main, ctx->s_main));
         CK(cudaEventRecord(ctx->ev_halo, ctx->s_main));
