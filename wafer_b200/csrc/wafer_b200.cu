@@ -382,6 +382,13 @@ struct PeerTargets {
 };
 // The time-tiled sweep can read h = (dt*v)/2 instead of V: same bytes, two DMULs less per site and sweep pair, at the price
 // of one more field in HBM.  Built lazily on the main stream; every launch of the sweep is ordered after it there.
+// The one-step TMA sweeps can read h too (WAFER_T1_HFIELD=1); measured: no difference for them (5/7-point, excited
+// steps within 0.5 %, gpurun_out/r2z) — they are not limited by those two multiplications — so it is off by default.
+bool t1_reads_h() {
+    static const bool on = getenv("WAFER_T1_HFIELD") && atoi(getenv("WAFER_T1_HFIELD")) == 1;
+    return on;
+}
+
 int ensure_hfield(wafer_ctx* ctx) {
     static const bool want = !(getenv("WAFER_TB_HFIELD") && atoi(getenv("WAFER_TB_HFIELD")) == 0);
     if (!want || ctx->h_valid) return WAFER_OK;
@@ -488,7 +495,7 @@ int launch_sweep_t1(wafer_ctx* ctx, int src, int xb, int xe, int mode, cudaStrea
     ex.nb_total = nb_total;
     ex.bid_off = bid_off;
     const bool sweep_mode = mode < t1::MODE_OBS || mode >= t1::MODE_CHK;
-    ex.hf = sweep_mode && ctx->h_valid ? 1 : 0;
+    ex.hf = t1_reads_h() && sweep_mode && ctx->h_valid ? 1 : 0;
     const CUtensorMap& tmv = ex.hf ? ctx->t1_h : ctx->t1_v;
     // the observables modes read psi[src] and store nothing: `out` only anchors the element offsets
     double* out = (mode >= t1::MODE_OBS && mode < t1::MODE_CHK) ? ctx->psi[src] : ctx->psi[src ^ 1];
@@ -1303,7 +1310,8 @@ static int wafer_evolve_impl(wafer_ctx* ctx, uint8_t wnum_in, uint64_t steps) {
     // hang): decide from the smallest slab of the decomposition, not from this rank's own L
     const bool overlap = ctx->world > 1 && !excited && ctx->min_L > 2 * g.gx;
     // (before the events below: the halo stream's launches must come after the build of h as well)
-    if ((ctx->use_tb || ctx->use_t1) && steps >= 4) TRY(ensure_hfield(ctx));  // one 16 B/site pass: pays for itself within a few sweeps
+    if (((ctx->use_tb && !excited) || (ctx->use_t1 && t1_reads_h())) && steps >= 4)
+        TRY(ensure_hfield(ctx));  // one 16 B/site pass: pays for itself after two sweep pairs
     if (overlap) {
         CK(cudaEventRecord(ctx->ev_main, ctx->s_main));
         CK(cudaEventRecord(ctx->ev_halo, ctx->s_main));
