@@ -81,6 +81,13 @@ int wafer_slab(const wafer_ctx *ctx, uint64_t *x0, uint64_t *x1); /* this rank's
    ranks own one plane more.  wafer_create uses exactly this. */
 int wafer_slab_partition(uint64_t nx, uint32_t world, uint32_t rank, uint64_t *x0, uint64_t *x1);
 
+/* Work distribution of the time-tiled sweep for a ny x nz plane over local x planes [xb, xe) on `slots` resident CTAs
+   (pure host arithmetic, no GPU needed — the rule wafer_evolve uses, exposed for the CPU tests): segments are rows of
+   5 ints {owner, y0, z0, xa, xz}; owner -1 = handed out in order through the kernel's atomic counter, owner k = static
+   tail of CTA k.  *n receives the number of segments (also when it exceeds cap). */
+int wafer_tb2_plan(uint32_t ny, uint32_t nz, int32_t xb, int32_t xe, uint32_t slots, int32_t *segments, uint64_t cap,
+                   uint64_t *n);
+
 /* -------- state in / out ------------------------------------------------------------------------ */
 /* Potentials{v,a,b} (potential.rs:14-25): uploads V and builds b = 1/(1+dt*v/2), a = (1-dt*v/2)*b
    (potential.rs:101-110) on the device. */

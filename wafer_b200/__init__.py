@@ -12,7 +12,7 @@ import numpy as np
 from . import _capi
 from ._capi import Observables, Params, Record
 
-__all__ = ["Lattice", "slab_partition", "WaferError", "POTENTIALS", "INITIAL_CONDITIONS", "EXT", "nccl_unique_id", "pinned_empty",
+__all__ = ["Lattice", "slab_partition", "tb2_plan", "WaferError", "POTENTIALS", "INITIAL_CONDITIONS", "EXT", "nccl_unique_id", "pinned_empty",
            "pin", "unpin", "FLAG_AB_ARRAYS"]
 
 # PotentialType (config.rs:74-104), InitialCondition (config.rs:153-170), CentralDifference.ext() (config.rs:232-238)
@@ -45,6 +45,20 @@ def slab_partition(nx, world, rank):
     if rc:
         raise WaferError(rc, "wafer_slab_partition(%d, %d, %d)" % (nx, world, rank))
     return x0.value, x1.value
+
+
+def tb2_plan(ny, nz, xb, xe, slots=148):
+    """work distribution of the time-tiled sweep (wafer_tb2_plan): array of rows [owner, y0, z0, xa, xz]"""
+    lib = _capi.load()
+    n = C.c_uint64()
+    rc = lib.wafer_tb2_plan(ny, nz, xb, xe, slots, None, 0, C.byref(n))
+    if rc:
+        raise WaferError(rc, "wafer_tb2_plan(%d, %d, %d, %d, %d)" % (ny, nz, xb, xe, slots))
+    out = np.zeros((n.value, 5), dtype=np.int32)
+    rc = lib.wafer_tb2_plan(ny, nz, xb, xe, slots, out.ctypes.data_as(C.POINTER(C.c_int32)), n.value, C.byref(n))
+    if rc:
+        raise WaferError(rc, "wafer_tb2_plan")
+    return out
 
 
 def nccl_unique_id():

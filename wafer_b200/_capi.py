@@ -34,6 +34,8 @@ SYMBOLS = {
     "wafer_slab": (C.c_int, [_ctx, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "wafer_slab_partition": (C.c_int, [C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64),
                                        C.POINTER(C.c_uint64)]),
+    "wafer_tb2_plan": (C.c_int, [C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, C.c_uint32, C.POINTER(C.c_int32), C.c_uint64,
+                                 C.POINTER(C.c_uint64)]),
     "wafer_set_potential": (C.c_int, [_ctx, _dp]),
     "wafer_get_potential": (C.c_int, [_ctx, _dp]),
     "wafer_set_pot_sub_scalar": (C.c_int, [_ctx, C.c_double]),

@@ -262,17 +262,17 @@ int init_tb(wafer_ctx* ctx) {
 // profiles/r2_tb2_variants.md): statically assigned rounds +4.8 % at 512^3 and +6 % on a 128-plane slab but -6 % at
 // 1024^3, where CTAs drift apart from round to round and the halo re-reads miss L2 (+17 % DRAM reads, ncu r2g); a fully
 // contiguous static split ("contig") -13 %.  WAFER_TB_SCHED=dynamic|rounds|legacy|contig selects the policy for A/B runs.
-int tb2_schedule(wafer_ctx* ctx, int xb, int xe, const Tb2Sched** out) {
-    auto it = ctx->tb2_sched.find({xb, xe});
-    if (it != ctx->tb2_sched.end()) { *out = &it->second; return WAFER_OK; }
-    const Geom& g = ctx->g;
-    const int ntz = ceil_div(g.nz, tb::TZ), nty = ceil_div(g.ny, tb::TY), ntiles = ntz * nty, P = xe - xb;
-    const int slots = ctx->sm_count * tb::CTAS_PER_SM;
+// pure host arithmetic (also behind wafer_tb2_plan for the CPU tests): bulk = in-order list, per[k] = static tail of CTA k
+struct Tb2Plan {
     std::vector<tb::Segment> bulk;
     std::vector<std::vector<tb::Segment>> per;
+};
+Tb2Plan tb2_plan(int ny, int nz, int xb, int xe, int slots, const std::string& mode, int MAXSEG) {
+    Tb2Plan pl;
+    std::vector<tb::Segment>& bulk = pl.bulk;
+    std::vector<std::vector<tb::Segment>>& per = pl.per;
+    const int ntz = ceil_div(nz, tb::TZ), nty = ceil_div(ny, tb::TY), ntiles = ntz * nty, P = xe - xb;
     auto seg = [&](int tile, int a, int b) { return tb::Segment{(tile / ntz) * tb::TY, (tile % ntz) * tb::TZ, a, b}; };
-    static const std::string mode = getenv("WAFER_TB_SCHED") ? getenv("WAFER_TB_SCHED") : "dynamic";
-    static const int MAXSEG = getenv("WAFER_TB_MAXSEG") ? std::max(8, atoi(getenv("WAFER_TB_MAXSEG"))) : 512;
     const int MINSEG = 6;
     int G = (int)std::max<long long>(1, std::min<long long>(slots, ((long long)ntiles * P + 7) / 8));
     // shares of `cols` tile columns starting at tile `t0`, planes [ca, cz), cut into G equal runs -> per[k]
@@ -309,10 +309,12 @@ int tb2_schedule(wafer_ctx* ctx, int xb, int xe, const Tb2Sched** out) {
             for (int t = 0; t < ntiles; ++t) bulk.push_back(seg(t, xb + c * chunk, std::min(xe, xb + (c + 1) * chunk)));
         G = (int)std::min<size_t>(slots, bulk.size());
         per.resize(G);
-    } else if (mode == "contig") {
+    } else if (mode == "contig" || (mode == "dynamic" && ntiles * 4 < G * 3)) {
+        // few tile columns on many CTAs (small planes: every halo lives in L2 anyway): one contiguous static run each
         per.resize(G);
         cut_static(0, ntiles, xb, xe);
     } else {
+        if (mode == "dynamic" && ntiles < G) G = ntiles;  // nearly one column per CTA: leave the few spare SMs idle, keep lock step
         per.resize(G);
         // number of x chunks: at least P / MAXSEG; a few more if that leaves a smaller statically cut tail.  The tail runs
         // out of lock step (its halo re-reads miss L2), which the estimate charges with an empirical factor of 1.6.
@@ -350,14 +352,24 @@ int tb2_schedule(wafer_ctx* ctx, int xb, int xe, const Tb2Sched** out) {
             }
         }
     }
+    return pl;
+}
+
+int tb2_schedule(wafer_ctx* ctx, int xb, int xe, const Tb2Sched** out) {
+    auto it = ctx->tb2_sched.find({xb, xe});
+    if (it != ctx->tb2_sched.end()) { *out = &it->second; return WAFER_OK; }
+    static const std::string mode = getenv("WAFER_TB_SCHED") ? getenv("WAFER_TB_SCHED") : "dynamic";
+    static const int MAXSEG = getenv("WAFER_TB_MAXSEG") ? std::max(8, atoi(getenv("WAFER_TB_MAXSEG"))) : 512;
+    const Tb2Plan pl = tb2_plan(ctx->g.ny, ctx->g.nz, xb, xe, ctx->sm_count * tb::CTAS_PER_SM, mode, MAXSEG);
+    const std::vector<tb::Segment>& bulk = pl.bulk;
     std::vector<tb::Segment> flat;
     std::vector<int> first{0};
-    for (const auto& v : per) {
+    for (const auto& v : pl.per) {
         flat.insert(flat.end(), v.begin(), v.end());
         first.push_back((int)flat.size());
     }
     Tb2Sched sc;
-    sc.ncta = G;
+    sc.ncta = (int)pl.per.size();
     sc.nbulk = (int)bulk.size();
     CK(cudaMalloc(&sc.bulk, std::max<size_t>(bulk.size(), 1) * sizeof(tb::Segment)));
     CK(cudaMalloc(&sc.segs, std::max<size_t>(flat.size(), 1) * sizeof(tb::Segment)));
@@ -1037,6 +1049,28 @@ int wafer_slab_partition(uint64_t nx, uint32_t world, uint32_t rank, uint64_t* x
     *x0 = rank * base + std::min<uint64_t>(rank, rem);
     *x1 = *x0 + base + (rank < rem ? 1 : 0);
     return WAFER_OK;
+}
+
+int wafer_tb2_plan(uint32_t ny, uint32_t nz, int32_t xb, int32_t xe, uint32_t slots, int32_t* segments, uint64_t cap, uint64_t* n) {
+    if (!n || ny == 0 || nz == 0 || xe <= xb || slots == 0) return WAFER_ERR_INVALID;
+    try {
+        const Tb2Plan pl = tb2_plan((int)ny, (int)nz, xb, xe, (int)slots, "dynamic", 512);
+        uint64_t k = 0;
+        auto put = [&](int owner, const tb::Segment& sg) {
+            if (segments && k < cap) {
+                int32_t* o = segments + 5 * k;
+                o[0] = owner; o[1] = sg.y0; o[2] = sg.z0; o[3] = sg.xa; o[4] = sg.xz;
+            }
+            ++k;
+        };
+        for (const auto& sg : pl.bulk) put(-1, sg);
+        for (size_t c = 0; c < pl.per.size(); ++c)
+            for (const auto& sg : pl.per[c]) put((int)c, sg);
+        *n = k;
+        return WAFER_OK;
+    } catch (const std::exception&) {
+        return WAFER_ERR_INVALID;
+    }
 }
 
 int wafer_slab(const wafer_ctx* ctx, uint64_t* x0, uint64_t* x1) {
