@@ -36,6 +36,14 @@ d=json.loads(open('$OUT/bench_quick.json').read().strip().splitlines()[-1]); pri
     sanitize)
       timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 3 python scripts/sanitize_small.py > "$OUT/memcheck.log" 2>&1; echo "memcheck rc=$?" | tee -a "$OUT/rc.log"; tail -2 "$OUT/memcheck.log"
       timeout 1500 compute-sanitizer --tool racecheck --error-exitcode 3 python scripts/sanitize_small.py > "$OUT/racecheck.log" 2>&1; echo "racecheck rc=$?" | tee -a "$OUT/rc.log"; tail -2 "$OUT/racecheck.log";;
+    ncu_tb2)
+      timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file "$OUT/launches.csv" \
+        python bench.py --grid 512 --sweeps 100 --steps 2 --warmup 1 --no-cpu --no-512 --no-parity > "$OUT/ncu_launch_bench.log" 2>&1
+      echo "ncu-launches rc=$?" | tee -a "$OUT/rc.log"
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:"sweep_tb2" -s 20 -c 1 -f -o "$OUT/tb2_full" \
+        python scripts/ncu_workload.py > "$OUT/ncu_tb2.log" 2>&1
+      echo "ncu-tb2 rc=$?" | tee -a "$OUT/rc.log"
+      ncu -i "$OUT/tb2_full.ncu-rep" --page raw --csv > "$OUT/tb2_full_raw.csv" 2>/dev/null;;
     c3)     WAFER_SLOW_TESTS=1 timeout 1500 python scripts/config_parity.py C3 --steps 50 --screen 50 > "$OUT/config_parity_C3.json" 2> "$OUT/config_parity_C3.err"; echo "c3 rc=$?" | tee -a "$OUT/rc.log"; tail -30 "$OUT/config_parity_C3.json";;
     c2)     timeout 900 python scripts/config_parity.py C2 --steps 50 --screen 50 > "$OUT/config_parity_C2.json" 2> "$OUT/config_parity_C2.err"; echo "c2 rc=$?" | tee -a "$OUT/rc.log"; tail -30 "$OUT/config_parity_C2.json";;
     extra)  N=512 M=512 timeout 900 python scripts/extra_bench.py > "$OUT/extra.json" 2> "$OUT/extra.err"; echo "extra rc=$?" | tee -a "$OUT/rc.log"; cat "$OUT/extra.json"; tail -3 "$OUT/extra.err";;
