@@ -35,6 +35,16 @@ def test_reference_arm_line():
     assert cb["spread"]["min"] <= cb["spread"]["median"] <= cb["spread"]["max"]
 
 
+def test_reference_arm_weak_scaling_workload():
+    """--workload C5 (BASELINE configs[4]): 2048 x 2048 x (256 per GPU), harmonic, weak scaling"""
+    r = _run(["--impl", "reference", "--workload", "C5", "--gpus", "8", "--steps", "1", "--warmup", "1", "--cpu-grid", "40",
+              "--cpu-lattice", "sample"])
+    assert r.returncode == 0, r.stderr
+    d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][0])
+    assert d["scaling"] == "weak" and d["config"]["grid"] == [2048, 2048, 2048] and "Harmonic" in d["config"]["workload"]
+    assert d["config"]["workload"].startswith("C5") and d["n_gpus"] == 8
+
+
 def test_reference_arm_other_ranks_do_nothing():
     r = _run(["--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1", "--cpu-grid", "32", "--cpu-lattice", "sample"], env={"RANK": "1"})
     assert r.returncode == 0 and r.stdout.strip() == ""
