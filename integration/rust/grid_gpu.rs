@@ -61,6 +61,7 @@ fn solve(config: &Config, log: &Logger, debug_level: usize, gpu: &Gpu, wnum: u8)
     let mut converged = false;
     let mut last_energy = MAX;
     let mut host_phi = Array3::<R64>::zeros((init_size[0], init_size[1], init_size[2]));
+    gpu.pin(&mut host_phi)?; // snapshots and the final save copy through this buffer
     loop {
         let o = gpu.check_state(wnum)?; // grid.rs:127-135 in one call
         let observables = ::grid::Observables {
@@ -107,6 +108,7 @@ fn solve(config: &Config, log: &Logger, debug_level: usize, gpu: &Gpu, wnum: u8)
             warn!(log, "Could not write wavefunction to disk: {}", err);
         }
     }
+    gpu.unpin(&mut host_phi);
     if converged {
         gpu.push_lower_from_phi()?; // grid.rs:241
         Ok(())
