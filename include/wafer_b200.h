@@ -155,9 +155,9 @@ int wafer_device_info(const wafer_ctx *ctx, char *name, size_t name_len, int32_t
                       int32_t *cc_minor, uint64_t *mem_bytes);
 /* Fused halo exchange over NVLink peer memory (optional, world > 1).  Every rank exports 192 bytes (CUDA IPC handles of
    its two psi buffers and its flag words), the host ships rank r-1's and rank r+1's blobs to rank r (NULL at the ends of
-   the chain) and calls connect.  From then on the boundary-plane launches of wafer_evolve store their results directly
-   into the neighbours' ghost planes and ranks order themselves with flag words in peer memory; without it the same
-   planes travel by ncclSend/ncclRecv. */
+   the chain) and calls connect.  From then on the ground-state sweep of wafer_evolve stores its first and last two output
+   planes directly into the neighbours' ghost planes as it produces them, and ranks order themselves with pass counters
+   in peer memory (one handshake per pass); without it the same planes travel by ncclSend/ncclRecv. */
 int wafer_p2p_export(wafer_ctx *ctx, uint8_t out[192]);
 int wafer_p2p_connect(wafer_ctx *ctx, const uint8_t *lower, const uint8_t *upper);
 /* self-test of the sweep's division by the loop-invariant denominator: compares it bit-for-bit with IEEE
@@ -168,8 +168,9 @@ int wafer_selftest_division(wafer_ctx *ctx, double den, uint64_t n, uint64_t see
    xor the out[1]s of all ranks to get the checksum of the union; equal checksums <=> bit-identical wavefunctions (up to
    2^-64 collisions).  This is how multi-GPU runs are compared bit-for-bit with a single-GPU run at full size. */
 int wafer_phi_checksum(wafer_ctx *ctx, uint64_t x_begin, uint64_t x_end, uint64_t out[2]);
-/* Fault injection for the multi-GPU ordering tests: stall this rank's halo stream by `nanoseconds` (<= 1e9) before
-   every boundary pass of wafer_evolve, so that its x-neighbours run ahead.  0 switches it off. */
+/* Fault injection for the multi-GPU ordering tests: stall this rank by `nanoseconds` (<= 1e9) before the halo handshake
+   of every pass of wafer_evolve (the main stream in the whole-column form, the halo stream in the split form), so that
+   its x-neighbours run ahead of it.  0 switches it off. */
 int wafer_debug_halo_delay(wafer_ctx *ctx, uint64_t nanoseconds);
 const char *wafer_version(void);
 const char *wafer_sweep_variant(const wafer_ctx *ctx); /* name of the sweep kernel variant in use */
