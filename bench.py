@@ -283,6 +283,13 @@ def parity_leg(lat, args, shape, phys, local_rank, rank, world, dist):
     dn, dt, mass = phys
     s = args.parity_sweeps
     other_flags = wafer_b200.FLAG_SIMPLE_SWEEP if world == 1 else args.flags
+    # the comparison run holds the WHOLE lattice on this GPU next to the slab: skip (and say so) when that cannot fit
+    field = (shape[0] + 4) * (shape[1] + 2) * (shape[2] + 16) * 8
+    need = 4.2 * field + 4.2 * field / world
+    total = lat.device_info()["mem_bytes"]
+    if need > 0.92 * total:
+        return {"skipped": "a single-GPU run of the whole %dx%dx%d lattice (%.0f GB with the slab) does not fit one GPU's %.0f GB"
+                           % (shape + (need / 1e9, total / 1e9)), "ok": None}
     x0, x1 = lat.slab
     lat.generate_potential(args.potential)
     lat.set_initial_conditions("Boolean")

@@ -33,7 +33,7 @@ std::string g_create_error;
 // scalar slots in ctx->scal (device doubles)
 // SL_RAW: [0] = sum psi^2 of the last excited-state sweep, [1 + i] = raw overlap sum q_i psi; SL_COEF: Gram-Schmidt s_i
 // SL_CHK: [sum psi^2, sum psi^2 potsub, sum psi^2 r2] left by the last sweep of a ground-state evolve (MODE_CHK)
-enum { SL_OBS = 0, SL_NORM = 4, SL_TMP = 5, SL_CHK = 8, SL_RAW = 16, SL_COEF = 16 + 256, SL_COUNT = 16 + 512 };
+enum { SL_OBS = 0, SL_TMP = 5, SL_CHK = 8, SL_RAW = 16, SL_COEF = 16 + 256, SL_COUNT = 16 + 512 };
 constexpr int GRAM_LD = 256;  // at most 255 stored states (wavenum is a u8)
 }  // namespace
 
