@@ -66,6 +66,9 @@ struct wafer_ctx {
     int potsub_mode = 0;
     double potsub_scalar = 0.0;
     std::vector<double*> lowers;
+    // CUDA graph of TWO excited-state steps (sweep + coefficients + projection, twice: the ping-pong parity returns), per
+    // (wnum, cur): small lattices are launch bound there (three dependent launches of a few microseconds per step)
+    std::map<std::pair<int, int>, std::pair<cudaGraphExec_t, int>> step_graphs;  // exec, kernel launches per replay
     bool chk_valid = false;    // scal[SL_CHK..] holds the point-wise check sums of the CURRENT psi (this rank's share)
     double* gram = nullptr;    // G[i][j] = <q_i, q_j>, j < i, of the stored states (device, GRAM_LD x GRAM_LD)
     // host <-> device: two small bounce buffers in the host layout, filled / drained on s_copy while the
@@ -96,6 +99,11 @@ struct wafer_ctx {
     mutable std::string err;
     size_t bytes() const { return (size_t)g.total() * sizeof(double); }
 };
+
+static void drop_step_graphs(wafer_ctx* ctx) {
+    for (auto& kv : ctx->step_graphs) cudaGraphExecDestroy(kv.second.first);
+    ctx->step_graphs.clear();
+}
 
 #define CK(call)                                                                                        \
     do {                                                                                                \
@@ -999,6 +1007,7 @@ int wafer_destroy(wafer_ctx* ctx) {
     if (!ctx) return WAFER_OK;
     if (ctx->s_main) cudaStreamSynchronize(ctx->s_main);
     if (ctx->s_halo) cudaStreamSynchronize(ctx->s_halo);
+    drop_step_graphs(ctx);
     if (ctx->comm) nccl_api().CommDestroy(ctx->comm);
     for (int n = 0; n < 2; ++n) {
         if (ctx->peer_psi[n][0]) cudaIpcCloseMemHandle(ctx->peer_psi[n][0]);
@@ -1246,6 +1255,7 @@ int wafer_clear_lowers(wafer_ctx* ctx) {
     CK(cudaStreamSynchronize(ctx->s_main));
     for (double* q : ctx->lowers) cudaFree(q);
     ctx->lowers.clear();
+    drop_step_graphs(ctx);  // they hold the freed pointers
     return WAFER_OK;
 }
 
@@ -1333,6 +1343,51 @@ int wafer_orthogonalise(wafer_ctx* ctx, uint8_t wnum) {
     return gs_apply(ctx, ctx->psi[ctx->cur], nullptr, n);
 }
 
+// one excited-state step on a single rank (grid.rs:567-681): sweep with the fused sums, then normalise + Gram-Schmidt
+static int excited_step(wafer_ctx* ctx, int wnum) {
+    const Geom& g = ctx->g;
+    const int src = ctx->cur;
+    const int nred = ctx->use_t1 ? 1 + std::min(wnum, t1::MAX_FUSED_LOWERS) : 1;
+    TRY(launch_sweep(ctx, ctx->psi[src], ctx->psi[src ^ 1], 0, g.L, nred, 0, ctx->s_main));
+    ctx->cur ^= 1;
+    return gs_apply(ctx, ctx->psi[src ^ 1], ctx->scal + SL_RAW, wnum, nred, sweep_blocks(ctx, 0, g.L));
+}
+
+
+// `pairs` times two excited-state steps through a captured graph.  Returns WAFER_OK with *ran = false when graphs are not
+// to be used (several ranks, switched off, or the capture failed: the caller then steps the ordinary way).
+static int excited_pairs_graph(wafer_ctx* ctx, int wnum, uint64_t pairs, bool* ran) {
+    *ran = false;
+    static const bool on = !(getenv("WAFER_GRAPHS") && atoi(getenv("WAFER_GRAPHS")) == 0);
+    if (!on || ctx->world != 1 || pairs == 0) return WAFER_OK;
+    const std::pair<int, int> key{wnum, ctx->cur};
+    auto it = ctx->step_graphs.find(key);
+    if (it == ctx->step_graphs.end()) {
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        const uint64_t launches0 = ctx->launches;
+        const int cur0 = ctx->cur;
+        if (cudaStreamBeginCapture(ctx->s_main, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return WAFER_OK; }
+        int rc = excited_step(ctx, wnum);
+        if (rc == WAFER_OK) rc = excited_step(ctx, wnum);
+        const cudaError_t ce = cudaStreamEndCapture(ctx->s_main, &graph);
+        const int per_pair = (int)(ctx->launches - launches0);
+        ctx->launches = launches0;  // nothing ran yet
+        ctx->cur = cur0;
+        if (rc != WAFER_OK || ce != cudaSuccess || !graph || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            return WAFER_OK;
+        }
+        cudaGraphDestroy(graph);
+        it = ctx->step_graphs.emplace(key, std::make_pair(exec, per_pair)).first;
+    }
+    for (uint64_t i = 0; i < pairs; ++i) CK(cudaGraphLaunch(it->second.first, ctx->s_main));
+    ctx->launches += pairs * (uint64_t)it->second.second;
+    *ran = true;
+    return WAFER_OK;
+}
+
 static int wafer_evolve_impl(wafer_ctx* ctx, uint8_t wnum_in, uint64_t steps) {
     if (!ctx) return WAFER_ERR_INVALID;
     TRY(ready(ctx, true));
@@ -1360,6 +1415,11 @@ static int wafer_evolve_impl(wafer_ctx* ctx, uint8_t wnum_in, uint64_t steps) {
     int chk_nb = 0;
     const int has_lo = ctx->rank > 0, has_hi = ctx->rank < ctx->world - 1;
     uint64_t done = 0;
+    if (excited && ctx->world == 1 && wnum <= t1::MAX_FUSED_LOWERS && total >= 8) {
+        bool ran = false;
+        TRY(excited_pairs_graph(ctx, wnum, total / 2, &ran));
+        if (ran) done = (total / 2) * 2;
+    }
     while (done < total) {
         // ground state: two steps per HBM pass with the time-tiled TMA kernel whenever two steps remain;
         // excited states need a global norm / Gram-Schmidt after EVERY step (grid.rs:674-681): one step per pass
