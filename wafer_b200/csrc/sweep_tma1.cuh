@@ -20,7 +20,7 @@
 #include "sweep_tb.cuh"
 
 #ifndef WAFER_T1_NPRE3
-#define WAFER_T1_NPRE3 2
+#define WAFER_T1_NPRE3 1  // measured at 512^3, k = 3 / 4: 1 -> 65.1 / 58.1 GLUPS, 0 -> 64.7 / 57.8, 2 -> 62.7 / 55.2 (gpurun_out/r2ae)
 #endif
 
 namespace wafer {
